@@ -15,6 +15,7 @@ _lib = None
 OV = {"random": 0, "degree": 1, "coarsen": 2}
 ON = {"asc": 0, "desc": 1, "random": 2}
 FLAG_FULL_CLIQUE = 1
+FLAG_SHARED_ORDER = 2
 
 
 def build():
@@ -41,6 +42,7 @@ def lib():
             ctypes.c_int64, P, P, P, ctypes.c_int64, P, P, ctypes.c_int, ctypes.c_int, ctypes.c_uint64,
             ctypes.c_uint32, ctypes.c_int, P, P, P, ctypes.c_int64, P, P]
         L.oracle_keyed_schur.restype = ctypes.c_int64
+        L.oracle_rank_perm.argtypes = [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, P]
         _lib = L
     return _lib
 
@@ -65,6 +67,12 @@ def ref_approximate_cholesky(edge_info, num_nodes, num_remove, o_v, o_n, sample_
 def philox(k0, k1, c0, c1, c2, c3):
     out = np.zeros(4, dtype=np.uint32)
     lib().oracle_philox4x32_10(k0, k1, c0, c1, c2, c3, out.ctypes.data)
+    return out
+
+
+def rank_perm(seed, graph, view, n_g):
+    out = np.zeros(n_g, dtype=np.uint32)
+    lib().oracle_rank_perm(seed, graph, view, n_g, out.ctypes.data)
     return out
 
 

@@ -457,9 +457,46 @@ enum { TAG_ORDER = 1, TAG_STAR = 2, TAG_PICK = 3 };
 
 static inline uint64_t mulhi64(uint64_t a, uint64_t b) { return (uint64_t)(((unsigned __int128)a * b) >> 64); }
 
+// o_v = random: rank(v) = position of v in a keyed pseudo-random permutation of its graph's vertices
+// (stands in for std::shuffle + pop, preconditioner.cc:588-613). 8-round balanced Feistel network over
+// the smallest even-width power-of-two domain covering n_g, cycle-walked into [0, n_g); round keys come
+// from Philox keyed on (seed; graph, view). The t vertices of lowest rank are eliminated in rank order.
+static inline uint32_t fmix32(uint32_t h) {
+    h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
+    return h;
+}
+struct RankPerm {
+    uint32_t rk[8];
+    uint32_t hb, mask, ng;
+    RankPerm(const Philox& ph, uint32_t graph, uint32_t view, uint32_t n_g) {
+        uint32_t o[4];
+        ph(graph, 0u, view, TAG_ORDER, o);
+        for (int r = 0; r < 4; r++) rk[r] = o[r];
+        ph(graph, 1u, view, TAG_ORDER, o);
+        for (int r = 0; r < 4; r++) rk[4 + r] = o[r];
+        uint32_t b = 2;
+        while (b < 32 && ((uint64_t)1 << b) < (uint64_t)n_g) b += 2;
+        hb = b / 2; mask = (hb >= 32) ? 0xffffffffu : ((1u << hb) - 1u); ng = n_g;
+    }
+    uint32_t perm(uint32_t x) const {
+        uint32_t L = x >> hb, R = x & mask;
+        for (int r = 0; r < 8; r++) {
+            uint32_t t = fmix32(R * 0x9E3779B1u + rk[r]) & mask;
+            uint32_t nr = L ^ t;
+            L = R; R = nr;
+        }
+        return (L << hb) | R;
+    }
+    uint32_t rank(uint32_t local) const {
+        uint32_t x = local;
+        do { x = perm(x); } while (x >= ng);
+        return x;
+    }
+};
+
 enum { OV_RANDOM = 0, OV_DEGREE = 1, OV_COARSEN = 2 };
 enum { ON_ASC = 0, ON_DESC = 1, ON_RANDOM = 2 };
-enum { FLAG_FULL_CLIQUE = 1 };
+enum { FLAG_FULL_CLIQUE = 1, FLAG_SHARED_ORDER = 2 };
 
 struct Entry { int32_t nbr; float w; };
 
@@ -695,18 +732,14 @@ int64_t oracle_keyed_schur(int64_t n, const int64_t* ptr, const int32_t* col, co
         int64_t b = graph_ptr[gi], e = graph_ptr[gi + 1], ng = e - b;
         int64_t t = std::min<int64_t>(std::max<int64_t>(num_remove[gi], 0), std::max<int64_t>(ng - 1, 0));
         if (o_v == OV_RANDOM) {
-            // the t smallest (ord(v), v) go, in ascending order: strictly sequential here; the CUDA path
+            // the t vertices of lowest rank go, in rank order: strictly sequential here; the CUDA path
             // runs any schedule that respects "lower-ranked adjacent vertex first" 
-            std::vector<std::pair<uint64_t, int32_t>> keys;
-            for (int64_t v = b; v < e; v++) {
-                uint32_t o[4];
-                ph((uint32_t)v, 0u, view, TAG_ORDER, o);
-                keys.push_back({((uint64_t)o[0] << 32) | o[1], (int32_t)v});
-            }
-            std::sort(keys.begin(), keys.end());
+            RankPerm rp(ph, (uint32_t)gi, (flags & FLAG_SHARED_ORDER) ? 0u : view, (uint32_t)ng);
+            std::vector<int32_t> by_rank((size_t)ng);
+            for (int64_t v = b; v < e; v++) by_rank[(size_t)rp.rank((uint32_t)(v - b))] = (int32_t)v;
             for (int64_t k = 0; k < t; k++) {
-                eliminate(g, keys[(size_t)k].second, o_v, o_n, flags, ph, view, st);
-                if (order_out) order_out[keys[(size_t)k].second] = (int32_t)k;
+                eliminate(g, by_rank[(size_t)k], o_v, o_n, flags, ph, view, st);
+                if (order_out) order_out[by_rank[(size_t)k]] = (int32_t)k;
             }
             st.rounds = std::max(st.rounds, t);
         } else {
@@ -751,3 +784,9 @@ int64_t oracle_keyed_schur(int64_t n, const int64_t* ptr, const int32_t* col, co
 }
 
 }  // extern "C"
+
+extern "C" void oracle_rank_perm(uint64_t seed, uint32_t graph, uint32_t view, uint32_t n_g, uint32_t* out) {
+    keyed::Philox ph{(uint32_t)seed, (uint32_t)(seed >> 32)};
+    keyed::RankPerm rp(ph, graph, view, n_g);
+    for (uint32_t v = 0; v < n_g; v++) out[v] = rp.rank(v);
+}

@@ -1,0 +1,446 @@
+// api.cu — the C ABI declared in include/rlap_b200.h: workspace layout, launch orchestration,
+// status handling and the host-buffer entry point that mirrors approximate_cholesky_cpu
+// (rlap/csrc/py_api_binder.cc:54-69).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/rlap_b200.h"
+#include "ingest.cuh"
+#include "scan.cuh"
+#include "schur.cuh"
+
+namespace rlap {
+cudaError_t launch_setup_graphs(int n, int G, const int* gptr, const long long* num_remove, int* gid, int* teff,
+                                cudaStream_t stream);
+cudaError_t eliminate_grid(int* blocks_out);
+cudaError_t launch_eliminate(const SchurParams& P, cudaStream_t stream);
+cudaError_t launch_emit_count(const SchurParams& P, long long* total_dev, cudaStream_t stream);
+cudaError_t launch_emit_write(const SchurParams& P, int* out_row, int* out_col, float* out_w, double* out_f64,
+                              cudaStream_t stream);
+}  // namespace rlap
+
+using namespace rlap;
+
+static thread_local std::string g_last_cuda_error;
+
+static int cuda_fail(cudaError_t e, const char* where) {
+    g_last_cuda_error = std::string(where) + ": " + cudaGetErrorString(e);
+    return RLAP_ERR_CUDA;
+}
+#define CK(call)                                                   \
+    do {                                                           \
+        cudaError_t _e = (call);                                   \
+        if (_e != cudaSuccess) return cuda_fail(_e, #call);        \
+    } while (0)
+
+// bump allocator over a caller-provided workspace (256-byte aligned pieces)
+struct Carver {
+    char* base;
+    size_t off;
+    explicit Carver(void* b) : base((char*)b), off(0) {}
+    template <typename T>
+    T* take(size_t count) {
+        off = (off + 255) & ~(size_t)255;
+        T* p = base ? (T*)(base + off) : (T*)nullptr;
+        off += count * sizeof(T);
+        return p;
+    }
+};
+
+extern "C" {
+
+const char* rlap_status_string(int s) {
+    switch (s) {
+        case RLAP_OK: return "ok";
+        case RLAP_ERR_INVALID_ARG: return "invalid argument";
+        case RLAP_ERR_ID_RANGE: return "node id out of range";
+        case RLAP_ERR_SELF_LOOP: return "self loop in edge list";
+        case RLAP_ERR_ASYMMETRIC: return "adjacency matrix is not symmetric";
+        case RLAP_ERR_POOL_OVERFLOW: return "fill-edge pool overflow (raise pool_cap)";
+        case RLAP_ERR_STAR_TOO_LARGE: return "vertex star larger than scratch capacity (raise scratch_cap)";
+        case RLAP_ERR_WORKSPACE: return "workspace too small";
+        case RLAP_ERR_CUDA: return "CUDA error";
+        case RLAP_ERR_NEGATIVE_WEIGHT: return "negative or non-finite edge weight";
+        default: return "unknown status";
+    }
+}
+const char* rlap_last_cuda_error(void) { return g_last_cuda_error.c_str(); }
+int rlap_version(void) { return 1; }
+
+// ------------------------------------------------------------------------------------------ ingest
+static long long ingest_scratch_cap(long long n, long long e) {
+    long long c = n > 4096 ? n : 4096;
+    if (c > e) c = e;
+    if (c < CAP_CTA + 1) c = CAP_CTA + 1;
+    return c;
+}
+
+struct IngestLayout {
+    IngestParams P;
+    size_t bytes;
+    int* zero_begin;
+    size_t zero_bytes;
+};
+
+static IngestLayout ingest_layout(long long n, long long e, void* ws) {
+    IngestLayout L;
+    memset(&L, 0, sizeof(L));
+    Carver c(ws);
+    IngestParams& P = L.P;
+    P.n = n;
+    P.e = e;
+    // zeroed block: cnt, cursor, small scalars
+    P.cnt = c.take<int>((size_t)n);
+    P.cursor = c.take<int>((size_t)n);
+    P.dl_tail = c.take<int>(1);
+    P.status = c.take<int>(1);
+    P.sym_acc = c.take<double>(2);
+    P.total_dev = c.take<long long>(1);
+    size_t zero_end = c.off;
+    L.zero_begin = P.cnt;
+    L.zero_bytes = zero_end;
+    P.rawptr = c.take<int>((size_t)n + 1);
+    P.cnt2 = c.take<int>((size_t)n);
+    P.rkey = c.take<uint64_t>((size_t)e);
+    P.rw = c.take<float>((size_t)e);
+    P.tcol = c.take<int>((size_t)e);
+    P.tw = c.take<float>((size_t)e);
+    P.dl = c.take<unsigned int>((size_t)n);
+    P.blocksum = c.take<long long>((size_t)scan_blocks(n));
+    P.scratch_cap = (int)ingest_scratch_cap(n, e);
+    P.scratch = c.take<uint64_t>((size_t)NSLOT * 3 * (size_t)P.scratch_cap);
+    L.bytes = c.off + 256;
+    return L;
+}
+
+int rlap_ingest_workspace_bytes(int64_t n, int64_t e, size_t* bytes) {
+    if (n < 0 || e < 0 || !bytes || n >= (1LL << 31) - 1 || e >= (1LL << 31) - 1) return RLAP_ERR_INVALID_ARG;
+    *bytes = ingest_layout(n, e, nullptr).bytes;
+    return RLAP_OK;
+}
+
+int rlap_ingest(const int64_t* src, const int64_t* dst, const float* w, int64_t e, int64_t n, int32_t* csr_ptr,
+                int32_t* csr_col, float* csr_w, int64_t* nnz_out, int flags, void* workspace, size_t workspace_bytes,
+                void* stream_v) {
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    if (n < 0 || e < 0 || n >= (1LL << 31) - 1 || e >= (1LL << 31) - 1 || !csr_ptr || !nnz_out || !workspace)
+        return RLAP_ERR_INVALID_ARG;
+    if (e > 0 && (!src || !dst || !csr_col || !csr_w)) return RLAP_ERR_INVALID_ARG;
+    IngestLayout L = ingest_layout(n, e, workspace);
+    if (workspace_bytes < L.bytes) return RLAP_ERR_WORKSPACE;
+    IngestParams& P = L.P;
+    P.src = (const long long*)src;
+    P.dst = (const long long*)dst;
+    P.w = w;
+    P.ptr = csr_ptr;
+    P.col = csr_col;
+    P.wout = csr_w;
+    P.validate = (flags & RLAP_FLAG_NO_VALIDATE) ? 0 : 1;
+    CK(cudaMemsetAsync(L.zero_begin, 0, L.zero_bytes, stream));
+    CK(launch_ingest_stage1(P, stream));
+    struct { int status; long long total; double acc[2]; } h;
+    CK(cudaMemcpyAsync(&h.status, P.status, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CK(cudaMemcpyAsync(&h.total, P.total_dev, sizeof(long long), cudaMemcpyDeviceToHost, stream));
+    CK(cudaMemcpyAsync(h.acc, P.sym_acc, 2 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    *nnz_out = h.total;
+    if (h.status != 0) return h.status;
+    // relative Frobenius tolerance 1e-6 (the reference uses Eigen's 1e-12 on float64 data)
+    if (P.validate && h.acc[0] > 1e-12 * h.acc[1]) return RLAP_ERR_ASYMMETRIC;
+    return RLAP_OK;
+}
+
+// ------------------------------------------------------------------------------------------- views
+struct SchurLayout {
+    SchurParams P;
+    size_t bytes;
+    int* gptr_dev;
+    long long* nrem_dev;
+    int* gid_dev;
+    int* teff_dev;
+    long long* total_dev;
+    long long* viewptr_dev;   // [V+1]
+    long long G, V, pool_cap, scratch_cap;
+};
+
+static long long default_pool_cap(long long nnz) { return 2 * nnz + 4096; }
+static long long default_scratch_cap(long long n) {
+    long long c = n < 65536 ? n : 65536;
+    if (c < CAP_CTA + 1) c = CAP_CTA + 1;
+    return c;
+}
+
+static SchurLayout schur_layout(long long n, long long nnz, long long G, long long V, long long pool_cap,
+                                long long scratch_cap, void* ws) {
+    SchurLayout L;
+    memset(&L, 0, sizeof(L));
+    if (pool_cap <= 0) pool_cap = default_pool_cap(nnz);
+    if (scratch_cap <= 0) scratch_cap = default_scratch_cap(n);
+    L.G = G; L.V = V; L.pool_cap = pool_cap; L.scratch_cap = scratch_cap;
+    Carver c(ws);
+    SchurParams& P = L.P;
+    const size_t VN = (size_t)V * (size_t)n, VG = (size_t)V * (size_t)G;
+    P.n = (int)n;
+    P.nnz = nnz;
+    P.G = (int)G;
+    P.V = (int)V;
+    P.ctr = c.take<int>(CTR_COUNT);
+    P.stats = c.take<unsigned long long>(ST_COUNT);
+    L.total_dev = c.take<long long>(1);
+    L.viewptr_dev = c.take<long long>((size_t)V + 1);
+    L.gptr_dev = c.take<int>((size_t)G + 1);
+    L.nrem_dev = c.take<long long>((size_t)G);
+    L.teff_dev = c.take<int>((size_t)G);
+    L.gid_dev = c.take<int>(G > 1 ? (size_t)n : 1);
+    P.state = c.take<uint8_t>(VN);
+    P.live = c.take<int>(VN);
+    P.head = c.take<int>(VN);
+    P.rank = c.take<int>(VN);
+    P.blk = c.take<int>(VN);
+    P.candround = c.take<int>(VN);
+    P.outcnt = c.take<int>(VN);
+    P.outoff = c.take<long long>(VN + 1);
+    P.pool = c.take<int4>((size_t)V * (size_t)pool_cap);
+    P.pool_cap = pool_cap;
+    P.pool_cursor = c.take<unsigned long long>((size_t)V);
+    P.rem = c.take<int>(VG);
+    P.minkey = c.take<int>(2 * VG);
+    P.cntI = c.take<int>(VG);
+    P.ovfseg = c.take<int>(VG);
+    P.thresh = c.take<unsigned int>(VG);
+    P.blockcnt = c.take<int>((VN + SEL_BLOCK - 1) / SEL_BLOCK + 1);
+    P.wl = c.take<unsigned int>(2 * VN + 1);
+    P.dl = c.take<unsigned int>(VN + 1);
+    P.scratch = c.take<uint64_t>((size_t)NSLOT * 3 * (size_t)scratch_cap);
+    P.scratch_cap = (int)scratch_cap;
+    P.blocksum = c.take<long long>((size_t)scan_blocks((long long)VN));
+    P.gptr = L.gptr_dev;
+    P.teff = L.teff_dev;
+    P.gid = G > 1 ? L.gid_dev : nullptr;
+    L.bytes = c.off + 256;
+    return L;
+}
+
+static int check_dims(int64_t n, int64_t nnz, int64_t G, int64_t V, int64_t pool_cap, int64_t scratch_cap) {
+    if (n < 1 || nnz < 0 || G < 1 || V < 1 || pool_cap < 0 || scratch_cap < 0) return RLAP_ERR_INVALID_ARG;
+    if (n >= (1LL << 31) - 1 || nnz >= (1LL << 31) - 1) return RLAP_ERR_INVALID_ARG;
+    if (V * n >= (1LL << 30)) return RLAP_ERR_INVALID_ARG;  // work-list positions are 32-bit
+    long long pc = pool_cap > 0 ? pool_cap : default_pool_cap(nnz);
+    if (pc >= (1LL << 31) - 1) return RLAP_ERR_INVALID_ARG;
+    if (G > n) return RLAP_ERR_INVALID_ARG;
+    return RLAP_OK;
+}
+
+int rlap_schur_workspace_bytes(int64_t n, int64_t nnz, int64_t n_graphs, int64_t n_views, int64_t pool_cap,
+                               int64_t scratch_cap, size_t* bytes) {
+    if (!bytes) return RLAP_ERR_INVALID_ARG;
+    int st = check_dims(n, nnz, n_graphs, n_views, pool_cap, scratch_cap);
+    if (st) return st;
+    *bytes = schur_layout(n, nnz, n_graphs, n_views, pool_cap, scratch_cap, nullptr).bytes;
+    return RLAP_OK;
+}
+
+static std::mutex g_layout_mutex;
+static std::unordered_map<void*, SchurLayout> g_layouts;  // workspace -> layout of the last eliminate call
+
+__global__ void k_gather_view_ptr(const long long* outoff, long long n, long long V, long long* viewptr) {
+    long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v <= V) viewptr[v] = outoff[v * n];
+}
+
+int rlap_schur_eliminate(int64_t n, int64_t nnz, const int32_t* csr_ptr, const int32_t* csr_col, const float* csr_w,
+                         int64_t n_graphs, const int64_t* graph_ptr, const int64_t* num_remove, int o_v, int o_n,
+                         uint64_t seed, int64_t view_base, int64_t n_views, int flags, int64_t pool_cap,
+                         int64_t scratch_cap, void* workspace, size_t workspace_bytes, int64_t* view_rows,
+                         int64_t* stats, void* stream_v) {
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    int st = check_dims(n, nnz, n_graphs, n_views, pool_cap, scratch_cap);
+    if (st) return st;
+    if (!csr_ptr || !graph_ptr || !num_remove || !workspace || !view_rows) return RLAP_ERR_INVALID_ARG;
+    if (nnz > 0 && (!csr_col || !csr_w)) return RLAP_ERR_INVALID_ARG;
+    if (o_v < 0 || o_v > 2 || o_n < 0 || o_n > 2 || view_base < 0) return RLAP_ERR_INVALID_ARG;
+    if (graph_ptr[0] != 0 || graph_ptr[n_graphs] != n) return RLAP_ERR_INVALID_ARG;
+    for (int64_t g = 0; g < n_graphs; g++)
+        if (graph_ptr[g + 1] < graph_ptr[g]) return RLAP_ERR_INVALID_ARG;
+    SchurLayout L = schur_layout(n, nnz, n_graphs, n_views, pool_cap, scratch_cap, workspace);
+    if (workspace_bytes < L.bytes) return RLAP_ERR_WORKSPACE;
+    SchurParams& P = L.P;
+    P.ptr = csr_ptr;
+    P.col = csr_col;
+    P.w = csr_w;
+    P.o_v = o_v;
+    P.o_n = o_n;
+    P.flags = flags;
+    P.k0 = (uint32_t)seed;
+    P.k1 = (uint32_t)(seed >> 32);
+    P.view_base = (uint32_t)view_base;
+    {
+        std::vector<int> gp((size_t)n_graphs + 1);
+        for (int64_t g = 0; g <= n_graphs; g++) gp[(size_t)g] = (int)graph_ptr[g];
+        CK(cudaMemcpyAsync(L.gptr_dev, gp.data(), sizeof(int) * gp.size(), cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(L.nrem_dev, num_remove, sizeof(long long) * (size_t)n_graphs, cudaMemcpyHostToDevice, stream));
+        CK(cudaStreamSynchronize(stream));  // gp is a local
+    }
+    CK(cudaMemsetAsync(P.ctr, 0, sizeof(int) * CTR_COUNT, stream));
+    CK(cudaMemsetAsync(P.stats, 0, sizeof(unsigned long long) * ST_COUNT, stream));
+    CK(launch_setup_graphs((int)n, (int)n_graphs, L.gptr_dev, L.nrem_dev, n_graphs > 1 ? L.gid_dev : nullptr, L.teff_dev,
+                           stream));
+    CK(launch_eliminate(P, stream));
+    CK(launch_emit_count(P, L.total_dev, stream));
+    k_gather_view_ptr<<<(unsigned)((n_views + 1 + 127) / 128), 128, 0, stream>>>(P.outoff, n, n_views, L.viewptr_dev);
+    CK(cudaGetLastError());
+    std::vector<long long> vp((size_t)n_views + 1);
+    int hctr[CTR_COUNT];
+    unsigned long long hstats[ST_COUNT];
+    std::vector<unsigned long long> hcur((size_t)n_views);
+    CK(cudaMemcpyAsync(vp.data(), L.viewptr_dev, sizeof(long long) * vp.size(), cudaMemcpyDeviceToHost, stream));
+    CK(cudaMemcpyAsync(hctr, P.ctr, sizeof(hctr), cudaMemcpyDeviceToHost, stream));
+    CK(cudaMemcpyAsync(hstats, P.stats, sizeof(hstats), cudaMemcpyDeviceToHost, stream));
+    CK(cudaMemcpyAsync(hcur.data(), P.pool_cursor, sizeof(unsigned long long) * hcur.size(), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    for (int64_t v = 0; v < n_views; v++) view_rows[v] = vp[(size_t)v + 1] - vp[(size_t)v];
+    if (stats) {
+        unsigned long long pmax = 0;
+        for (auto c : hcur) pmax = c > pmax ? c : pmax;
+        stats[0] = hctr[CTR_ROUNDS];
+        stats[1] = (int64_t)hstats[ST_FILLS];
+        stats[2] = (int64_t)pmax;
+        stats[3] = (int64_t)hstats[ST_MAXSTAR];
+        stats[4] = (int64_t)hstats[ST_RAW];
+        stats[5] = vp[(size_t)n_views];
+        stats[6] = L.pool_cap;
+        stats[7] = 0;
+    }
+    {
+        std::lock_guard<std::mutex> lk(g_layout_mutex);
+        g_layouts[workspace] = L;
+    }
+    if (hctr[CTR_STATUS] != 0) return hctr[CTR_STATUS];
+    return RLAP_OK;
+}
+
+int rlap_schur_emit(int64_t n, int64_t nnz, const int32_t* csr_ptr, const int32_t* csr_col, const float* csr_w,
+                    int64_t n_views, void* workspace, size_t workspace_bytes, int32_t* out_row, int32_t* out_col,
+                    float* out_w, double* out_f64, void* stream_v) {
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    SchurLayout L;
+    {
+        std::lock_guard<std::mutex> lk(g_layout_mutex);
+        auto it = g_layouts.find(workspace);
+        if (it == g_layouts.end()) return RLAP_ERR_INVALID_ARG;
+        L = it->second;
+    }
+    if (L.P.n != n || L.P.nnz != nnz || L.V != n_views || workspace_bytes < L.bytes) return RLAP_ERR_INVALID_ARG;
+    if (L.P.ptr != csr_ptr || L.P.col != csr_col || L.P.w != csr_w) return RLAP_ERR_INVALID_ARG;
+    if ((out_row || out_col || out_w) && !(out_row && out_col && out_w)) return RLAP_ERR_INVALID_ARG;
+    if (!out_row && !out_f64) return RLAP_ERR_INVALID_ARG;
+    CK(launch_emit_write(L.P, out_row, out_col, out_w, out_f64, stream));
+    return RLAP_OK;
+}
+
+// --------------------------------------------------------------------------- host-buffer entry point
+__global__ void k_unpack_edge_info(const double* ei, long long e, long long* src, long long* dst, float* w) {
+    long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < e) {
+        src[p] = (long long)ei[p * 3 + 0];
+        dst[p] = (long long)ei[p * 3 + 1];
+        w[p] = (float)ei[p * 3 + 2];
+    }
+}
+
+struct DevBuf {
+    void* p = nullptr;
+    cudaStream_t s;
+    explicit DevBuf(cudaStream_t st) : s(st) {}
+    cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes ? bytes : 1, s); }
+    ~DevBuf() { if (p) cudaFreeAsync(p, s); }
+};
+
+int rlap_approximate_cholesky_host(const double* edge_info, int64_t e, int64_t num_nodes, int64_t num_remove,
+                                   const char* o_v, const char* o_n, uint64_t seed, double** out, int64_t* rows) {
+    if (!out || !rows || !o_v || !o_n || e < 0 || num_nodes < 1 || (e > 0 && !edge_info)) return RLAP_ERR_INVALID_ARG;
+    int ov = !strcmp(o_v, "random") ? 0 : !strcmp(o_v, "degree") ? 1 : !strcmp(o_v, "coarsen") ? 2 : -1;
+    int on = !strcmp(o_n, "asc") ? 0 : !strcmp(o_n, "desc") ? 1 : !strcmp(o_n, "random") ? 2 : -1;
+    if (ov < 0 || on < 0) return RLAP_ERR_INVALID_ARG;
+    static bool pool_set = false;
+    if (!pool_set) {  // keep freed blocks cached in the default pool: repeated calls do not hit cudaMalloc
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaMemPool_t mp;
+        if (cudaDeviceGetDefaultMemPool(&mp, dev) == cudaSuccess) {
+            uint64_t thr = UINT64_MAX;
+            cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+        pool_set = true;
+    }
+    cudaStream_t s = 0;
+    *out = nullptr;
+    *rows = 0;
+    const int64_t n = num_nodes;
+    DevBuf d_ei(s), d_src(s), d_dst(s), d_w(s), d_ptr(s), d_col(s), d_cw(s), d_ws(s), d_ws2(s), d_out(s);
+    CK(d_ei.alloc(sizeof(double) * 3 * (size_t)e));
+    CK(d_src.alloc(sizeof(long long) * (size_t)e));
+    CK(d_dst.alloc(sizeof(long long) * (size_t)e));
+    CK(d_w.alloc(sizeof(float) * (size_t)e));
+    CK(d_ptr.alloc(sizeof(int) * ((size_t)n + 1)));
+    CK(d_col.alloc(sizeof(int) * (size_t)e));
+    CK(d_cw.alloc(sizeof(float) * (size_t)e));
+    size_t wsb = 0;
+    int st = rlap_ingest_workspace_bytes(n, e, &wsb);
+    if (st) return st;
+    CK(d_ws.alloc(wsb));
+    if (e > 0) {
+        CK(cudaMemcpyAsync(d_ei.p, edge_info, sizeof(double) * 3 * (size_t)e, cudaMemcpyHostToDevice, s));
+        k_unpack_edge_info<<<(unsigned)((e + 255) / 256), 256, 0, s>>>((const double*)d_ei.p, e, (long long*)d_src.p,
+                                                                      (long long*)d_dst.p, (float*)d_w.p);
+        CK(cudaGetLastError());
+    }
+    int64_t nnz = 0;
+    st = rlap_ingest((const int64_t*)d_src.p, (const int64_t*)d_dst.p, (const float*)d_w.p, e, n, (int32_t*)d_ptr.p,
+                     (int32_t*)d_col.p, (float*)d_cw.p, &nnz, 0, d_ws.p, wsb, s);
+    if (st) return st;
+    int64_t gp[2] = {0, n};
+    int64_t nr[1] = {num_remove};
+    int64_t vrows = 0;
+    int64_t pool_cap = 0;
+    size_t wsb2 = 0;
+    for (int attempt = 0;; attempt++) {
+        st = rlap_schur_workspace_bytes(n, nnz, 1, 1, pool_cap, 0, &wsb2);
+        if (st) return st;
+        DevBuf ws2(s);
+        CK(ws2.alloc(wsb2));
+        st = rlap_schur_eliminate(n, nnz, (int32_t*)d_ptr.p, (int32_t*)d_col.p, (float*)d_cw.p, 1, gp, nr, ov, on, seed,
+                                  0, 1, 0, pool_cap, 0, ws2.p, wsb2, &vrows, nullptr, s);
+        if (st == RLAP_ERR_POOL_OVERFLOW && attempt < 6) {
+            pool_cap = (pool_cap ? pool_cap : 2 * nnz + 4096) * 2;
+            continue;
+        }
+        if (st) return st;
+        CK(d_out.alloc(sizeof(double) * 3 * (size_t)vrows));
+        st = rlap_schur_emit(n, nnz, (int32_t*)d_ptr.p, (int32_t*)d_col.p, (float*)d_cw.p, 1, ws2.p, wsb2, nullptr,
+                             nullptr, nullptr, (double*)d_out.p, s);
+        if (st) return st;
+        double* h = (double*)malloc(sizeof(double) * 3 * (size_t)(vrows > 0 ? vrows : 1));
+        if (!h) return RLAP_ERR_INVALID_ARG;
+        CK(cudaMemcpyAsync(h, d_out.p, sizeof(double) * 3 * (size_t)vrows, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        {
+            std::lock_guard<std::mutex> lk(g_layout_mutex);
+            g_layouts.erase(ws2.p);
+        }
+        *out = h;
+        *rows = vrows;
+        return RLAP_OK;
+    }
+}
+
+void rlap_free_host(void* p) { free(p); }
+
+}  // extern "C"

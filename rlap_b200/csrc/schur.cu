@@ -1,0 +1,859 @@
+// schur.cu — ordering, elimination and emission kernels of the rLap randomized Schur complement.
+//
+// Replaces {Random,Priority,Coarsening}Preconditioner::getSchurComplement
+// (rlap/csrc/preconditioner.cc:348-476, 713-825, 835-957) with a round-parallel design:
+//   * the graph is an immutable coalesced CSR shared by all views; every view keeps only
+//     per-vertex state, a head pointer per vertex and an append-only pool of fill entries
+//     (lazy deletion: an entry dies when the vertex it points to is eliminated);
+//   * one persistent cooperative kernel runs ALL rounds of ALL views (grid.sync between phases);
+//   * inside a round, vertices that are pairwise non-adjacent are eliminated concurrently, one warp
+//     (or one thread block for big stars) per vertex: gather -> fixed-point quantise -> bitonic sort
+//     by neighbour -> merge multi-edges -> o_n sort -> warp-shuffle prefix sums -> Philox-driven
+//     binary-search sampling -> atomic append of the fill edges to both endpoints.
+// The sequential specification this file implements bit for bit is oracle/rlap_oracle.cc (keyed mode)
+// and DESIGN.md §3.
+#include <cooperative_groups.h>
+#include "rlap_device.cuh"
+#include "schur.cuh"
+#include "scan.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace rlap {
+
+__device__ __forceinline__ void set_status(const SchurParams& P, int code) { atomicCAS(P.ctr + CTR_STATUS, 0, code); }
+
+__device__ __forceinline__ int graph_of(const SchurParams& P, int v) { return P.gid ? __ldg(P.gid + v) : 0; }
+
+// key of the degree bucket queue (preconditioner.cc:125-246 restated): number of live
+// list entries, never below 1 once the vertex had an edge (DegreePQDec is a no-op at key 1), 0 for
+// vertices that were isolated from the start.
+__device__ __forceinline__ int key_eff(const SchurParams& P, size_t vb, int v) {
+    int d0 = __ldg(P.ptr + v + 1) - __ldg(P.ptr + v);
+    if (d0 == 0) return 0;
+    return max(ldcg_i32(P.live + vb + v), 1);
+}
+__device__ __forceinline__ int key_nbr(const SchurParams& P, size_t vb, int u) {  // u has an edge: deg0 > 0
+    return max(ldcg_i32(P.live + vb + u), 1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// star staging
+// ---------------------------------------------------------------------------------------------
+
+// Gather the raw live entries of v into sb.A (unordered). Returns their count (group uniform);
+// *wmaxb receives the bit pattern of the largest weight. Entries beyond sb.cap are counted, not stored.
+template <bool CTA>
+__device__ int star_gather(const SchurParams& P, int view, int v, StarBuf sb, CtaScratch* cs, uint32_t* wmaxb_out) {
+    const size_t vb = (size_t)view * (size_t)P.n;
+    const uint8_t* st = P.state + vb;
+    const int4* pool = P.pool + (size_t)view * (size_t)P.pool_cap;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const int b = __ldg(P.ptr + v), e = __ldg(P.ptr + v + 1);
+    uint32_t wmaxb = 0;
+    int cnt = 0;
+    if (CTA) {
+        if (threadIdx.x == 0) cs->icount = 0;
+        __syncthreads();
+    }
+    // base CSR segment: coalesced
+    const int stride = g_size<CTA>();
+    for (int p0 = b; p0 < e; p0 += stride) {
+        int p = p0 + g_rank<CTA>();
+        bool ok = p < e;
+        int u = 0;
+        float w = 0.f;
+        if (ok) {
+            u = __ldg(P.col + p);
+            ok = ldcg_u8(st + u) != 2;
+        }
+        if (ok) w = __ldg(P.w + p);
+        unsigned m = __ballot_sync(RLAP_FULL_MASK, ok);
+        int base;
+        if (CTA) {
+            base = 0;
+            if (lane == 0 && m) base = atomicAdd(&cs->icount, __popc(m));
+            base = __shfl_sync(RLAP_FULL_MASK, base, 0);
+        } else {
+            base = cnt;
+            cnt += __popc(m);
+        }
+        if (ok) {
+            int pos = base + __popc(m & lt);
+            if (pos < sb.cap) sb.A[pos] = pack_a((uint32_t)u, w);
+            wmaxb = max(wmaxb, __float_as_uint(w));
+        }
+    }
+    // appended fill entries: a linked list, walked by one warp; 32 hops are collected before the
+    // (dependent) state lookups so that those run in parallel
+    if (!CTA || (threadIdx.x >> 5) == 0) {
+        int p = ldcg_i32(P.head + vb + v);
+        while (p >= 0) {
+            int4 mine = make_int4(0, 0, 0, 0);
+            bool have = false;
+            for (int k = 0; k < 32 && p >= 0; k++) {
+                int4 en = __ldcg(pool + p);
+                if (lane == k) { mine = en; have = true; }
+                p = en.z;
+            }
+            bool ok = have && (ldcg_u8(st + mine.x) != 2);
+            unsigned m = __ballot_sync(RLAP_FULL_MASK, ok);
+            int base;
+            if (CTA) {
+                base = 0;
+                if (lane == 0 && m) base = atomicAdd(&cs->icount, __popc(m));
+                base = __shfl_sync(RLAP_FULL_MASK, base, 0);
+            } else {
+                base = cnt;
+                cnt += __popc(m);
+            }
+            if (ok) {
+                int pos = base + __popc(m & lt);
+                if (pos < sb.cap) sb.A[pos] = pack_a((uint32_t)mine.x, __int_as_float(mine.y));
+                wmaxb = max(wmaxb, (uint32_t)mine.y);
+            }
+        }
+    }
+    if (CTA) {
+        __syncthreads();
+        cnt = cs->icount;
+    }
+    *wmaxb_out = g_max_u32<CTA>(wmaxb, cs);
+    g_sync<CTA>();
+    return cnt;
+}
+
+// Quantise, pad to a power of two, sort by neighbour and merge multi-edges in place: the first entry
+// of every run keeps the summed fixed-point weight (and, if the run has more than one entry, the
+// dequantised fp32 weight); the others are marked dead (weight word RLAP_DEAD_W, Q = 0) but keep the
+// neighbour id. Returns the number of distinct neighbours; *P2_out = padded length.
+template <bool CTA>
+__device__ int star_sort_merge(StarBuf sb, int lraw, int shift, CtaScratch* cs, int* P2_out) {
+    const int gs = g_size<CTA>(), r = g_rank<CTA>();
+    const int P2 = next_pow2(lraw);
+    for (int i = r; i < P2; i += gs) {
+        if (i < lraw) {
+            sb.Q[i] = quantize(a_w(sb.A[i]), shift);
+        } else {
+            sb.A[i] = RLAP_PAD_A;
+            sb.Q[i] = 0;
+        }
+        sb.K[i] = ~0ull;
+    }
+    g_sync<CTA>();
+    g_bitonic_sort<CTA, SORT_BY_A>(sb, P2);
+    int L = 0;
+    if (CTA) {
+        if (threadIdx.x == 0) cs->icount = 0;
+        __syncthreads();
+    }
+    const int lane = threadIdx.x & 31;
+    for (int base = 0; base < lraw; base += gs) {
+        int i = base + r;
+        bool act = i < lraw;
+        uint64_t a = act ? sb.A[i] : RLAP_PAD_A;
+        uint32_t nb = a_nbr(a);
+        bool headf = act && (i == 0 || a_nbr(sb.A[i - 1]) != nb);
+        unsigned long long qs = 0;
+        int c = 0;
+        if (headf) {
+            int j = i;
+            do { qs += sb.Q[j]; c++; j++; } while (j < lraw && a_nbr(sb.A[j]) == nb);
+        }
+        unsigned m = __ballot_sync(RLAP_FULL_MASK, headf);
+        g_sync<CTA>();  // every read of this chunk's runs is done before anything is rewritten
+        if (act) {
+            if (headf) {
+                sb.Q[i] = qs;
+                if (c > 1) sb.A[i] = ((uint64_t)nb << 32) | (uint64_t)__float_as_uint(dequantize(qs, shift));
+            } else {
+                sb.Q[i] = 0;
+                sb.A[i] = ((uint64_t)nb << 32) | (uint64_t)RLAP_DEAD_W;
+            }
+        }
+        if (CTA) {
+            if (lane == 0 && m) atomicAdd(&cs->icount, __popc(m));
+        } else {
+            L += __popc(m);
+        }
+    }
+    g_sync<CTA>();
+    if (CTA) L = cs->icount;
+    g_sync<CTA>();
+    *P2_out = P2;
+    return L;
+}
+
+__device__ __forceinline__ void push_entry(const SchurParams& P, size_t vb, int4* pool, int owner, int nbr, float w,
+                                           int slot) {
+    int4 en;
+    en.x = nbr;
+    en.y = __float_as_int(w);
+    en.z = atomicExch(P.head + vb + owner, slot);
+    en.w = owner;
+    pool[slot] = en;
+    atomicAdd(P.live + vb + owner, 1);
+}
+
+// fill edge (j,k,w): append to both endpoints; o_v = random also records the new dependency
+__device__ __forceinline__ void push_fill(const SchurParams& P, size_t vb, int4* pool, int j, int k, float w,
+                                          long long slot) {
+    if (!(w > 0.f)) return;
+    push_entry(P, vb, pool, j, k, w, (int)slot);
+    push_entry(P, vb, pool, k, j, w, (int)slot + 1);
+    if (P.o_v == 0) {
+        if (ldcg_u8(P.state + vb + j) == 1 && ldcg_u8(P.state + vb + k) == 1) {
+            int rj = ldcg_i32(P.rank + vb + j), rk = ldcg_i32(P.rank + vb + k);
+            if (rj < rk) atomicAdd(P.blk + vb + k, 1); else atomicAdd(P.blk + vb + j, 1);
+        }
+    }
+}
+
+// Eliminate vertex v of `view` (A.2 clique sampling / A.4 coarsening / full clique), DESIGN.md §3.3.
+template <bool CTA>
+__device__ void eliminate_star(const SchurParams& P, const RoundCtx& rc, int view, int v, StarBuf sb, CtaScratch* cs) {
+    const size_t vb = (size_t)view * (size_t)P.n;
+    const int gs = g_size<CTA>(), r = g_rank<CTA>();
+    const uint32_t view_id = P.view_base + (uint32_t)view;
+    int4* pool = P.pool + (size_t)view * (size_t)P.pool_cap;
+    uint32_t wmaxb;
+    int lraw = star_gather<CTA>(P, view, v, sb, cs, &wmaxb);
+    if (lraw > sb.cap) {  // cannot happen for the smem tiers (callers check live); scratch tier: report
+        if (r == 0) set_status(P, 6);
+        lraw = 0;  // leave the vertex in place; the run is invalid anyway
+        g_sync<CTA>();
+        return;
+    }
+    int P2 = 0, L = 0;
+    if (lraw > 0) {
+        const int shift = star_shift(__uint_as_float(wmaxb), lraw);
+        L = star_sort_merge<CTA>(sb, lraw, shift, cs, &P2);
+        const bool full = (P.flags & 1) != 0;
+        const bool coarsen = (P.o_v == 2) && !full;
+        const int on = coarsen ? 2 : P.o_n;
+        if (!full && on == 2) {
+            for (int i = r; i < lraw; i += gs) {
+                uint64_t a = sb.A[i];
+                if (!a_dead(a)) {
+                    uint4 x = philox4x32_10(P.k0, P.k1, (uint32_t)v, a_nbr(a), view_id, TAG_STAR);
+                    sb.K[i] = ((uint64_t)x.z << 32) | (uint64_t)x.w;
+                }
+            }
+            g_sync<CTA>();
+        }
+        if (full || on == 0) g_bitonic_sort<CTA, SORT_ASC>(sb, P2);
+        else if (on == 1) g_bitonic_sort<CTA, SORT_DESC>(sb, P2);
+        else g_bitonic_sort<CTA, SORT_KEY>(sb, P2);
+        g_incl_scan_u64<CTA>(sb.Q, sb.K, L, cs);
+        const unsigned long long S = sb.K[L - 1];
+        // ---- fill edges
+        long long nf = full ? (long long)L * (L - 1) / 2 : (long long)(L - 1);
+        long long slot0 = 0;
+        bool ovf = false;
+        if (nf > 0) {
+            if (CTA) {
+                if (threadIdx.x == 0) cs->carry = atomicAdd(P.pool_cursor + view, (unsigned long long)(2 * nf));
+                __syncthreads();
+                slot0 = (long long)cs->carry;
+            } else {
+                unsigned long long s0 = 0;
+                if (r == 0) s0 = atomicAdd(P.pool_cursor + view, (unsigned long long)(2 * nf));
+                slot0 = (long long)__shfl_sync(RLAP_FULL_MASK, s0, 0);
+            }
+            ovf = slot0 + 2 * nf > P.pool_cap;
+            if (ovf && r == 0) set_status(P, 5);
+        }
+        if (nf > 0 && !ovf) {
+            if (full) {
+                const double Sf = __dmul_rn(__ull2double_rn(S), pow2d(-shift));
+                for (int a = 0; a < L - 1; a++) {
+                    const uint64_t ea = sb.A[a];
+                    const long long off = (long long)a * (2LL * L - a - 1) / 2;
+                    for (int b2 = a + 1 + r; b2 < L; b2 += gs) {
+                        const uint64_t eb = sb.A[b2];
+                        float w = __double2float_rn(__ddiv_rn(__dmul_rn((double)a_w(ea), (double)a_w(eb)), Sf));
+                        push_fill(P, vb, pool, (int)a_nbr(ea), (int)a_nbr(eb), w, slot0 + 2 * (off + (b2 - a - 1)));
+                    }
+                }
+            } else if (coarsen) {
+                uint4 x = philox4x32_10(P.k0, P.k1, (uint32_t)v, 0xffffffffu, view_id, TAG_PICK);
+                unsigned long long u = ((unsigned long long)x.x << 32) | (unsigned long long)x.y;
+                unsigned long long rr = __umul64hi(u, S);
+                int koff = upper_bound_u64(sb.K, L, rr);
+                if (koff >= L) koff = L - 1;
+                const uint64_t ek = sb.A[koff];
+                const double wk = (double)a_w(ek);
+                for (int m = r; m < L; m += gs) {
+                    if (m == koff) continue;
+                    const uint64_t em = sb.A[m];
+                    const double wm = (double)a_w(em);
+                    float w = __double2float_rn(__ddiv_rn(__dmul_rn(wk, wm), __dadd_rn(wk, wm)));
+                    int sl = m < koff ? m : m - 1;
+                    push_fill(P, vb, pool, (int)a_nbr(em), (int)a_nbr(ek), w, slot0 + 2LL * sl);
+                }
+            } else {
+                for (int m = r; m < L - 1; m += gs) {
+                    const uint64_t em = sb.A[m];
+                    const unsigned long long Cm = sb.K[m];
+                    const unsigned long long rem = S - Cm;
+                    uint4 x = philox4x32_10(P.k0, P.k1, (uint32_t)v, a_nbr(em), view_id, TAG_STAR);
+                    unsigned long long u = ((unsigned long long)x.x << 32) | (unsigned long long)x.y;
+                    unsigned long long rr = Cm + __umul64hi(u, rem);
+                    int koff = upper_bound_u64(sb.K, L, rr);
+                    if (koff >= L) koff = L - 1;
+                    float w = __double2float_rn(
+                        __ddiv_rn(__dmul_rn((double)a_w(em), __ull2double_rn(rem)), __ull2double_rn(S)));
+                    push_fill(P, vb, pool, (int)a_nbr(em), (int)a_nbr(sb.A[koff]), w, slot0 + 2LL * m);
+                }
+            }
+        }
+        // every push (and, for o_v = random, every dependency increment) is ordered before the
+        // decrements below: a neighbour's counter can only reach zero once all its lower-ranked
+        // eventual neighbours are gone
+        __threadfence();
+        g_sync<CTA>();
+        for (int i = r; i < P2; i += gs) {
+            uint64_t a = sb.A[i];
+            if (a == RLAP_PAD_A) continue;
+            int u = (int)a_nbr(a);
+            atomicSub(P.live + vb + u, 1);
+            if (P.o_v == 0 && ldcg_u8(P.state + vb + u) == 1) {
+                int old = atomicSub(P.blk + vb + u, 1);
+                if (old == 1) {
+                    int pos = rc.wl_base + atomicAdd(P.ctr + rc.wslot, 1);
+                    P.wl[pos] = (unsigned int)(vb + (size_t)u);
+                }
+            }
+        }
+        if (r == 0) {
+            atomicAdd(P.stats + ST_FILLS, (unsigned long long)(ovf ? 0 : nf));
+            atomicMax(P.stats + ST_MAXSTAR, (unsigned long long)L);
+            atomicAdd(P.stats + ST_RAW, (unsigned long long)lraw);
+        }
+    }
+    if (r == 0) {
+        P.state[vb + v] = 2;
+        if (P.o_v != 0) atomicSub(P.rem + (size_t)view * P.G + graph_of(P, v), 1);
+    }
+    g_sync<CTA>();
+}
+
+__device__ __forceinline__ StarBuf warp_buf(uint64_t* smem) {
+    int w = threadIdx.x >> 5;
+    StarBuf sb;
+    sb.A = smem + (size_t)w * 3 * CAP_WARP;
+    sb.Q = sb.A + CAP_WARP;
+    sb.K = sb.Q + CAP_WARP;
+    sb.cap = CAP_WARP;
+    return sb;
+}
+__device__ __forceinline__ StarBuf cta_buf(uint64_t* smem) {
+    StarBuf sb;
+    sb.A = smem;
+    sb.Q = smem + CAP_CTA;
+    sb.K = smem + 2 * CAP_CTA;
+    sb.cap = CAP_CTA;
+    return sb;
+}
+__device__ __forceinline__ StarBuf scratch_buf(const SchurParams& P) {
+    StarBuf sb;
+    sb.A = P.scratch + (size_t)blockIdx.x * 3 * (size_t)P.scratch_cap;
+    sb.Q = sb.A + P.scratch_cap;
+    sb.K = sb.Q + P.scratch_cap;
+    sb.cap = P.scratch_cap;
+    return sb;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the persistent elimination kernel
+// ---------------------------------------------------------------------------------------------
+
+// process work-list items [start, end): one warp per item; big stars are deferred to the block phase
+__device__ void run_warp_items(const SchurParams& P, const RoundCtx& rc, uint64_t* smem, CtaScratch* cs, int start,
+                               int end) {
+    const int gw = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int nw = (int)((gridDim.x * blockDim.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    StarBuf sb = warp_buf(smem);
+    for (int it = start + gw; it < end; it += nw) {
+        unsigned int idx = __ldcg(P.wl + it);
+        int view = (int)(idx / (unsigned)P.n), v = (int)(idx % (unsigned)P.n);
+        if (P.o_v != 0) {  // truncated final round of a graph: only the highest ids go
+            size_t seg = (size_t)view * P.G + graph_of(P, v);
+            if (ldcg_i32(P.ovfseg + seg) && idx < __ldcg(P.thresh + seg)) continue;
+        }
+        int lv = ldcg_i32(P.live + idx);
+        if (lv <= CAP_WARP) {
+            eliminate_star<false>(P, rc, view, v, sb, cs);
+        } else if (lane == 0) {
+            int pos = rc.dl_base + atomicAdd(P.ctr + rc.dslot, 1);
+            P.dl[pos] = idx;
+        }
+    }
+}
+
+// deferred items [start, end): one block per item in shared memory; stars beyond CAP_CTA go to the
+// NSLOT blocks that own a global scratch slot
+__device__ void run_block_items(const SchurParams& P, const RoundCtx& rc, uint64_t* smem, CtaScratch* cs, int start,
+                                int end) {
+    for (int it = start + (int)blockIdx.x; it < end; it += (int)gridDim.x) {
+        unsigned int idx = __ldcg(P.dl + it);
+        int view = (int)(idx / (unsigned)P.n), v = (int)(idx % (unsigned)P.n);
+        if (ldcg_i32(P.live + idx) <= CAP_CTA) eliminate_star<true>(P, rc, view, v, cta_buf(smem), cs);
+        __syncthreads();
+    }
+    if ((int)blockIdx.x < NSLOT) {
+        int j = 0;
+        for (int it = start; it < end; it++) {
+            unsigned int idx = __ldcg(P.dl + it);
+            if (ldcg_i32(P.live + idx) <= CAP_CTA) continue;
+            if ((j++ % NSLOT) != (int)blockIdx.x) continue;
+            int view = (int)(idx / (unsigned)P.n), v = (int)(idx % (unsigned)P.n);
+            eliminate_star<true>(P, rc, view, v, scratch_buf(P), cs);
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
+    extern __shared__ __align__(16) uint64_t smem[];
+    __shared__ CtaScratch cs;
+    cg::grid_group grid = cg::this_grid();
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nthr = (long long)gridDim.x * blockDim.x;
+    const long long VN = (long long)P.V * P.n;
+    const long long VG = (long long)P.V * P.G;
+    const bool random_order = (P.o_v == 0);
+
+    // ---- init: per-vertex state (ordering kernel for o_v = random: keyed Feistel rank)
+    for (long long idx = tid; idx < VN; idx += nthr) {
+        int view = (int)(idx / P.n), v = (int)(idx % P.n);
+        P.live[idx] = __ldg(P.ptr + v + 1) - __ldg(P.ptr + v);
+        P.head[idx] = -1;
+        if (random_order) {
+            int g = graph_of(P, v);
+            int gb = __ldg(P.gptr + g), ng = __ldg(P.gptr + g + 1) - gb;
+            RankPerm rp;
+            uint32_t oview = (P.flags & 2) ? 0u : (P.view_base + (uint32_t)view);
+            rp.init(P.k0, P.k1, (uint32_t)g, oview, (uint32_t)ng);
+            int rk = (int)rp.rank((uint32_t)(v - gb));
+            P.rank[idx] = rk;
+            P.state[idx] = rk < __ldg(P.teff + g) ? 1 : 0;
+        } else {
+            P.state[idx] = 1;
+            P.candround[idx] = -1;
+        }
+    }
+    if (!random_order) {
+        for (long long s = tid; s < VG; s += nthr) {
+            int g = (int)(s % P.G);
+            P.rem[s] = __ldg(P.teff + g);
+            P.minkey[s] = 0x7fffffff;
+            P.minkey[VG + s] = 0x7fffffff;
+            P.cntI[s] = 0;
+            P.ovfseg[s] = 0;
+        }
+    }
+    for (long long s = tid; s < P.V; s += nthr) P.pool_cursor[s] = 0ull;
+    grid.sync();
+
+    int wl_start = 0;   // first unconsumed work-list item
+    int dl_start = 0;
+    int rounds = 0;
+    RoundCtx rc;
+
+    if (random_order) {
+        // dependency counters: pending lower-ranked eligible neighbours; roots seed the work list
+        // (they count as appended in round -1, i.e. on counter slot 2)
+        for (long long idx = tid; idx < VN; idx += nthr) {
+            if (ldcg_u8(P.state + idx) != 1) continue;
+            int view = (int)(idx / P.n), v = (int)(idx % P.n);
+            size_t vb = (size_t)view * P.n;
+            int rv = ldcg_i32(P.rank + idx);
+            int c = 0;
+            for (int p = __ldg(P.ptr + v), e = __ldg(P.ptr + v + 1); p < e; p++) {
+                int u = __ldg(P.col + p);
+                if (ldcg_u8(P.state + vb + u) == 1 && ldcg_i32(P.rank + vb + u) < rv) c++;
+            }
+            P.blk[idx] = c;
+            if (c == 0) {
+                int pos = atomicAdd(P.ctr + CTR_WCNT0 + 2, 1);
+                P.wl[pos] = (unsigned int)idx;
+            }
+        }
+        grid.sync();
+        while (true) {
+            // items to consume were appended in the previous round
+            int wl_end = wl_start + ldcg_i32(P.ctr + CTR_WCNT0 + (rounds + 2) % 3);
+            if (wl_end == wl_start) break;
+            if (tid == 0) { P.ctr[CTR_WCNT0 + (rounds + 1) % 3] = 0; P.ctr[CTR_DCNT0 + (rounds + 1) % 3] = 0; }
+            rc.wl_base = wl_end; rc.wslot = CTR_WCNT0 + rounds % 3;
+            rc.dl_base = dl_start; rc.dslot = CTR_DCNT0 + rounds % 3;
+            run_warp_items(P, rc, smem, &cs, wl_start, wl_end);
+            wl_start = wl_end;
+            grid.sync();
+            int dl_end = dl_start + ldcg_i32(P.ctr + rc.dslot);
+            if (dl_end != dl_start) {
+                run_block_items(P, rc, smem, &cs, dl_start, dl_end);
+                dl_start = dl_end;
+                grid.sync();
+            }
+            rounds++;
+        }
+    } else {
+        // degree / coarsen: rounds over the minimum-key bucket of every (view, graph) segment
+        while (true) {
+            const int par = rounds & 1;
+            int* mk = P.minkey + (size_t)par * VG;
+            int* mk_other = P.minkey + (size_t)(par ^ 1) * VG;
+            rc.wl_base = wl_start; rc.wslot = CTR_WCNT0 + rounds % 3;
+            rc.dl_base = dl_start; rc.dslot = CTR_DCNT0 + rounds % 3;
+            // phase A: minimum key per segment
+            if (tid == 0) {
+                P.ctr[CTR_ACTIVE0 + (par ^ 1)] = 0; P.ctr[CTR_OVF0 + (par ^ 1)] = 0;
+                P.ctr[CTR_WCNT0 + (rounds + 1) % 3] = 0; P.ctr[CTR_DCNT0 + (rounds + 1) % 3] = 0;
+            }
+            for (long long s = tid; s < VG; s += nthr) { mk_other[s] = 0x7fffffff; P.cntI[s] = 0; P.ovfseg[s] = 0; }
+            for (long long idx = tid; idx < VN; idx += nthr) {
+                if (ldcg_u8(P.state + idx) == 2) continue;
+                int view = (int)(idx / P.n), v = (int)(idx % P.n);
+                size_t seg = (size_t)view * P.G + graph_of(P, v);
+                if (ldcg_i32(P.rem + seg) <= 0) continue;
+                atomicMin(mk + seg, key_eff(P, (size_t)view * P.n, v));
+                P.ctr[CTR_ACTIVE0 + par] = 1;
+            }
+            grid.sync();
+            if (ldcg_i32(P.ctr + CTR_ACTIVE0 + par) == 0) break;
+            // phase B: members of the minimum bucket with no bucket neighbour of higher id
+            for (long long idx = tid; idx < VN; idx += nthr) {
+                if (ldcg_u8(P.state + idx) == 2) continue;
+                int view = (int)(idx / P.n), v = (int)(idx % P.n);
+                size_t vb = (size_t)view * P.n;
+                size_t seg = (size_t)view * P.G + graph_of(P, v);
+                int rm = ldcg_i32(P.rem + seg);
+                if (rm <= 0) continue;
+                int m = ldcg_i32(mk + seg);
+                if (key_eff(P, vb, v) != m) continue;
+                bool ok = true;
+                for (int p = __ldg(P.ptr + v), e = __ldg(P.ptr + v + 1); p < e && ok; p++) {
+                    int u = __ldg(P.col + p);
+                    if (u > v && ldcg_u8(P.state + vb + u) != 2 && key_nbr(P, vb, u) == m) ok = false;
+                }
+                const int4* pool = P.pool + (size_t)view * (size_t)P.pool_cap;
+                for (int p = ldcg_i32(P.head + idx); p >= 0 && ok;) {
+                    int4 en = __ldcg(pool + p);
+                    if (en.x > v && ldcg_u8(P.state + vb + en.x) != 2 && key_nbr(P, vb, en.x) == m) ok = false;
+                    p = en.z;
+                }
+                if (!ok) continue;
+                P.candround[idx] = rounds;
+                int pos = rc.wl_base + atomicAdd(P.ctr + rc.wslot, 1);
+                P.wl[pos] = (unsigned int)idx;
+                int c = atomicAdd(P.cntI + seg, 1);
+                if (c + 1 > rm) P.ctr[CTR_OVF0 + par] = 1;
+            }
+            grid.sync();
+            // phase C: a graph that selected more than it may still remove keeps its highest ids
+            if (ldcg_i32(P.ctr + CTR_OVF0 + par)) {
+                const int gw = (int)(tid >> 5), nw = (int)(nthr >> 5), lane = threadIdx.x & 31;
+                const long long nblk = (VN + SEL_BLOCK - 1) / SEL_BLOCK;
+                for (long long bk = gw; bk < nblk; bk += nw) {
+                    int c = 0;
+                    for (int j = 0; j < SEL_BLOCK / 32; j++) {
+                        long long idx = bk * SEL_BLOCK + j * 32 + lane;
+                        bool f = idx < VN && ldcg_i32(P.candround + idx) == rounds;
+                        c += __popc(__ballot_sync(RLAP_FULL_MASK, f));
+                    }
+                    if (lane == 0) P.blockcnt[bk] = c;
+                }
+                grid.sync();
+                for (long long s = gw; s < VG; s += nw) {
+                    int need = ldcg_i32(P.rem + s);
+                    if (ldcg_i32(P.cntI + s) <= need) continue;
+                    int view = (int)(s / P.G), g = (int)(s % P.G);
+                    long long lo = (long long)view * P.n + __ldg(P.gptr + g);
+                    long long hi = (long long)view * P.n + __ldg(P.gptr + g + 1);  // exclusive
+                    // walk down from hi in SEL_BLOCK-aligned pieces until `need` candidates are covered
+                    long long cur = hi;
+                    int acc = 0;
+                    long long T = lo;
+                    while (cur > lo) {
+                        long long pb = ((cur - 1) / SEL_BLOCK) * SEL_BLOCK;  // aligned block holding cur-1
+                        long long pstart = pb > lo ? pb : lo;
+                        bool whole = (pstart == pb) && (cur == pb + SEL_BLOCK);
+                        int c;
+                        if (whole) {
+                            c = ldcg_i32(P.blockcnt + pb / SEL_BLOCK);
+                        } else {
+                            c = 0;
+                            for (long long q0 = pstart; q0 < cur; q0 += 32) {
+                                long long q = q0 + lane;
+                                bool f = q < cur && ldcg_i32(P.candround + q) == rounds;
+                                c += __popc(__ballot_sync(RLAP_FULL_MASK, f));
+                            }
+                        }
+                        if (acc + c >= need) {
+                            // the threshold lies inside [pstart, cur): scan it from the top, 32 ids at a time
+                            long long q1 = cur;
+                            while (q1 > pstart) {
+                                long long q0 = q1 - 32 > pstart ? q1 - 32 : pstart;
+                                long long q = q0 + lane;
+                                bool f = q < q1 && ldcg_i32(P.candround + q) == rounds;
+                                unsigned mb = __ballot_sync(RLAP_FULL_MASK, f);
+                                int cc = __popc(mb);
+                                if (acc + cc >= need) {
+                                    int want = need - acc;  // keep the `want` highest set bits of mb
+                                    int bit = 31;
+                                    for (;; bit--) {
+                                        if (mb & (1u << bit)) { want--; if (want == 0) break; }
+                                    }
+                                    T = q0 + bit;
+                                    acc = need;
+                                    break;
+                                }
+                                acc += cc;
+                                q1 = q0;
+                            }
+                            break;
+                        }
+                        acc += c;
+                        cur = pstart;
+                    }
+                    if (lane == 0) { P.thresh[s] = (unsigned int)T; P.ovfseg[s] = 1; }
+                }
+                grid.sync();
+            }
+            // phase D: eliminate
+            int wl_end = wl_start + ldcg_i32(P.ctr + rc.wslot);
+            run_warp_items(P, rc, smem, &cs, wl_start, wl_end);
+            wl_start = wl_end;
+            grid.sync();
+            int dl_end = dl_start + ldcg_i32(P.ctr + rc.dslot);
+            if (dl_end != dl_start) {
+                run_block_items(P, rc, smem, &cs, dl_start, dl_end);
+                dl_start = dl_end;
+                grid.sync();
+            }
+            rounds++;
+        }
+    }
+    if (tid == 0) P.ctr[CTR_ROUNDS] = rounds;
+}
+
+// ---------------------------------------------------------------------------------------------
+// emission (A.5): surviving vertices, multi-edges merged, neighbours ascending
+// ---------------------------------------------------------------------------------------------
+template <bool CTA, bool WRITE>
+__device__ void emit_star(const SchurParams& P, int view, int v, StarBuf sb, CtaScratch* cs, int* out_row, int* out_col,
+                          float* out_w, double* out_f64) {
+    const size_t vb = (size_t)view * (size_t)P.n;
+    const int gs = g_size<CTA>(), r = g_rank<CTA>();
+    uint32_t wmaxb;
+    int lraw = star_gather<CTA>(P, view, v, sb, cs, &wmaxb);
+    if (lraw > sb.cap) {
+        if (r == 0) { set_status(P, 6); if (!WRITE) P.outcnt[vb + v] = 0; }
+        g_sync<CTA>();
+        return;
+    }
+    int L = 0, P2 = 0;
+    if (lraw > 0) {
+        const int shift = star_shift(__uint_as_float(wmaxb), lraw);
+        L = star_sort_merge<CTA>(sb, lraw, shift, cs, &P2);
+    }
+    if (!WRITE) {
+        if (r == 0) P.outcnt[vb + v] = L;
+    } else if (L > 0) {
+        const long long off = P.outoff[vb + v];
+        const int lane = threadIdx.x & 31;
+        int carry = 0;
+        for (int base = 0; base < lraw; base += gs) {
+            int i = base + r;
+            uint64_t a = (i < lraw) ? sb.A[i] : RLAP_PAD_A;
+            bool live = (i < lraw) && !a_dead(a);
+            unsigned m = __ballot_sync(RLAP_FULL_MASK, live);
+            int pos = __popc(m & ((1u << lane) - 1u));
+            if (CTA) {
+                int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+                __syncthreads();
+                if (lane == 0) cs->wsum[w] = (unsigned long long)__popc(m);
+                __syncthreads();
+                int add = 0, tot = 0;
+                for (int k = 0; k < nw; k++) { int c = (int)cs->wsum[k]; if (k < w) add += c; tot += c; }
+                pos += add + carry;
+                carry += tot;
+            } else {
+                pos += carry;
+                carry += __popc(m);
+            }
+            if (live) {
+                long long o = off + pos;
+                if (out_row) { out_row[o] = (int)a_nbr(a); out_col[o] = v; out_w[o] = a_w(a); }
+                if (out_f64) {
+                    out_f64[o * 3 + 0] = (double)a_nbr(a);
+                    out_f64[o * 3 + 1] = (double)v;
+                    out_f64[o * 3 + 2] = (double)a_w(a);
+                }
+            }
+        }
+    }
+    g_sync<CTA>();
+}
+
+template <bool WRITE>
+__global__ void __launch_bounds__(BLOCK_THREADS, 2) k_emit_warp(SchurParams P, int* out_row, int* out_col, float* out_w,
+                                                               double* out_f64) {
+    extern __shared__ __align__(16) uint64_t smem[];
+    __shared__ CtaScratch cs;
+    const long long VN = (long long)P.V * P.n;
+    const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    StarBuf sb = warp_buf(smem);
+    // a warp takes 32 consecutive vertices, keeps the ones that have rows and serves them one by one
+    for (long long base = gw * 32; base < VN; base += nw * 32) {
+        long long idx = base + lane;
+        int lv = 0;
+        bool alive = false;
+        if (idx < VN) {
+            alive = P.state[idx] != 2;
+            lv = alive ? P.live[idx] : 0;
+            if (!WRITE && !(alive && lv > 0)) P.outcnt[idx] = 0;
+            if (WRITE && alive && lv > 0 && P.outcnt[idx] == 0) lv = 0;
+        }
+        bool big = lv > CAP_WARP;
+        if (!WRITE && big) {
+            int pos = atomicAdd(P.ctr + CTR_EMIT_DL, 1);
+            P.dl[pos] = (unsigned int)idx;
+        }
+        unsigned todo = __ballot_sync(RLAP_FULL_MASK, lv > 0 && !big);
+        while (todo) {
+            int k = __ffs(todo) - 1;
+            todo &= todo - 1;
+            long long id2 = base + k;
+            emit_star<false, WRITE>(P, (int)(id2 / P.n), (int)(id2 % P.n), sb, &cs, out_row, out_col, out_w, out_f64);
+        }
+    }
+}
+
+template <bool WRITE>
+__global__ void __launch_bounds__(BLOCK_THREADS, 2) k_emit_block(SchurParams P, int* out_row, int* out_col, float* out_w,
+                                                                double* out_f64) {
+    extern __shared__ __align__(16) uint64_t smem[];
+    __shared__ CtaScratch cs;
+    int end = P.ctr[CTR_EMIT_DL];
+    for (int it = (int)blockIdx.x; it < end; it += (int)gridDim.x) {
+        unsigned int idx = P.dl[it];
+        int view = (int)(idx / (unsigned)P.n), v = (int)(idx % (unsigned)P.n);
+        if (P.live[idx] <= CAP_CTA) emit_star<true, WRITE>(P, view, v, cta_buf(smem), &cs, out_row, out_col, out_w, out_f64);
+        __syncthreads();
+    }
+    if ((int)blockIdx.x < NSLOT) {
+        int j = 0;
+        for (int it = 0; it < end; it++) {
+            unsigned int idx = P.dl[it];
+            if (P.live[idx] <= CAP_CTA) continue;
+            if ((j++ % NSLOT) != (int)blockIdx.x) continue;
+            int view = (int)(idx / (unsigned)P.n), v = (int)(idx % (unsigned)P.n);
+            emit_star<true, WRITE>(P, view, v, scratch_buf(P), &cs, out_row, out_col, out_w, out_f64);
+            __syncthreads();
+        }
+    }
+}
+
+// gid[v] = graph of vertex v, teff[g] = min(max(num_remove, 0), n_g - 1)
+__global__ void k_setup_graphs(int n, int G, const int* gptr, const long long* num_remove, int* gid, int* teff) {
+    long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid < G) {
+        long long ng = gptr[tid + 1] - gptr[tid];
+        long long t = num_remove[tid];
+        if (t < 0) t = 0;
+        if (t > ng - 1) t = ng - 1;
+        if (t < 0) t = 0;
+        teff[tid] = (int)t;
+    }
+    if (gid && tid < n) {
+        int lo = 0, hi = G;  // last g with gptr[g] <= v
+        while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (gptr[mid] <= (int)tid) lo = mid; else hi = mid;
+        }
+        gid[tid] = lo;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-side launchers (called from api.cu)
+// ---------------------------------------------------------------------------------------------
+static const size_t kSmemBytes = (size_t)3 * CAP_CTA * sizeof(uint64_t);
+
+cudaError_t launch_setup_graphs(int n, int G, const int* gptr, const long long* num_remove, int* gid, int* teff,
+                                cudaStream_t stream) {
+    long long work = n > G ? n : G;
+    int blocks = (int)((work + 255) / 256);
+    if (blocks < 1) blocks = 1;
+    k_setup_graphs<<<blocks, 256, 0, stream>>>(n, G, gptr, num_remove, gid, teff);
+    return cudaGetLastError();
+}
+
+cudaError_t eliminate_grid(int* blocks_out) {
+    static int cached = 0;
+    if (!cached) {
+        cudaError_t e = cudaFuncSetAttribute(k_eliminate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+        if (e != cudaSuccess) return e;
+        int dev = 0, sms = 0, occ = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_eliminate, BLOCK_THREADS, kSmemBytes);
+        if (e != cudaSuccess) return e;
+        if (occ < 1) return cudaErrorLaunchOutOfResources;
+        cached = sms * occ;
+    }
+    *blocks_out = cached;
+    return cudaSuccess;
+}
+
+cudaError_t launch_eliminate(const SchurParams& P, cudaStream_t stream) {
+    int blocks = 0;
+    cudaError_t e = eliminate_grid(&blocks);
+    if (e != cudaSuccess) return e;
+    SchurParams Pc = P;
+    void* args[] = {(void*)&Pc};
+    return cudaLaunchCooperativeKernel((void*)k_eliminate, dim3(blocks), dim3(BLOCK_THREADS), args, kSmemBytes, stream);
+}
+
+template <bool WRITE>
+static cudaError_t launch_emit_pass(const SchurParams& P, int* out_row, int* out_col, float* out_w, double* out_f64,
+                                    cudaStream_t stream) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(k_emit_warp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+        cudaFuncSetAttribute(k_emit_warp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+        cudaFuncSetAttribute(k_emit_block<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+        cudaFuncSetAttribute(k_emit_block<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+        attr_done = true;
+    }
+    int blocks = 0;
+    cudaError_t e = eliminate_grid(&blocks);  // same block shape: reuse the resident-grid size
+    if (e != cudaSuccess) return e;
+    k_emit_warp<WRITE><<<blocks, BLOCK_THREADS, kSmemBytes, stream>>>(P, out_row, out_col, out_w, out_f64);
+    k_emit_block<WRITE><<<blocks, BLOCK_THREADS, kSmemBytes, stream>>>(P, out_row, out_col, out_w, out_f64);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_emit_count(const SchurParams& P, long long* total_dev, cudaStream_t stream) {
+    // the deferred list is reused: reset its tail first
+    cudaError_t e = cudaMemsetAsync(P.ctr + CTR_EMIT_DL, 0, sizeof(int), stream);
+    if (e != cudaSuccess) return e;
+    e = launch_emit_pass<false>(P, nullptr, nullptr, nullptr, nullptr, stream);
+    if (e != cudaSuccess) return e;
+    long long VN = (long long)P.V * P.n;
+    return launch_exclusive_scan<long long>(P.outcnt, VN, P.outoff, P.blocksum, total_dev, stream);
+}
+
+cudaError_t launch_emit_write(const SchurParams& P, int* out_row, int* out_col, float* out_w, double* out_f64,
+                              cudaStream_t stream) {
+    return launch_emit_pass<true>(P, out_row, out_col, out_w, out_f64, stream);
+}
+
+}  // namespace rlap

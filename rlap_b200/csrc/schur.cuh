@@ -1,0 +1,91 @@
+// schur.cuh — parameter block shared by the elimination / emission kernels and the C-ABI layer.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rlap {
+
+// tiers: a star with at most CAP_WARP raw live entries is handled by one warp in shared memory,
+// up to CAP_CTA by one thread block in shared memory (the block's warp buffers overlaid), larger
+// ones by one thread block in its global-memory scratch slot (up to scratch_cap).
+constexpr int BLOCK_THREADS = 512;
+constexpr int WARPS_PER_BLOCK = BLOCK_THREADS / 32;
+constexpr int CAP_WARP = 128;
+constexpr int CAP_CTA = CAP_WARP * WARPS_PER_BLOCK;  // 2048
+constexpr int SEL_BLOCK = 1024;                       // ids per block of the truncation search
+
+constexpr int NSLOT = 8;                              // blocks that own a global scratch slot
+
+// Work lists are append-only over the whole run. Items appended during round r land at
+// base + atomicAdd(ctr[CTR_WCNT0 + r % 3]); the base is a value every block knows, and a counter
+// is only read after the grid barrier that ends its round and reset two rounds later, so no block
+// ever reads a count that another block may still be bumping.
+enum {
+    CTR_WCNT0 = 0,       // work-list appends, rotating by round % 3
+    CTR_DCNT0 = 3,       // deferred (big star) appends, rotating by round % 3
+    CTR_STATUS = 6,      // first error seen by a kernel (rlap_status)
+    CTR_ACTIVE0 = 7,     // degree mode: any segment still active, by round parity
+    CTR_ACTIVE1 = 8,
+    CTR_OVF0 = 9,        // degree mode: some segment selected more candidates than it may remove
+    CTR_OVF1 = 10,
+    CTR_ROUNDS = 11,
+    CTR_EMIT_DL = 12,    // emission: deferred list tail
+    CTR_COUNT = 16
+};
+
+struct RoundCtx {
+    int wl_base;   // where items appended in this round start
+    int wslot;     // ctr index of this round's work-list counter
+    int dl_base;
+    int dslot;
+};
+enum { ST_FILLS = 0, ST_POOL_MAX = 1, ST_MAXSTAR = 2, ST_DEFERRED = 3, ST_RAW = 4, ST_COUNT = 8 };
+
+struct SchurParams {
+    // coalesced graph (shared by all views, immutable)
+    int n;
+    long long nnz;
+    const int* ptr;
+    const int* col;
+    const float* w;
+    int G;
+    const int* gptr;   // [G+1]
+    const int* teff;   // [G] min(num_remove, n_g - 1)
+    const int* gid;    // [n] graph of a vertex, or nullptr when G == 1
+    // run
+    int o_v, o_n, flags;
+    uint32_t k0, k1;
+    uint32_t view_base;
+    int V;
+    // per view state, all indexed [view * n + v]
+    uint8_t* state;    // 0 kept (not eligible), 1 pending, 2 eliminated
+    int* live;         // number of raw entries whose neighbour is not eliminated
+    int* head;         // head of the appended fill-entry list (pool index, -1 = empty)
+    int* rank;         // o_v = random: rank in the keyed permutation
+    int* blk;          // o_v = random: pending lower-ranked eligible neighbours (raw multiplicity)
+    int* candround;    // degree / coarsen: last round in which the vertex was selected
+    int* outcnt;       // emission: merged row count
+    long long* outoff; // emission: [V*n + 1] exclusive prefix of outcnt
+    // fill-entry pool: pool[view * pool_cap + p] = {nbr, weight bits, next, owner}
+    int4* pool;
+    long long pool_cap;
+    unsigned long long* pool_cursor;  // [V]
+    // per (view, graph) segment state, indexed [view * G + g]   (degree / coarsen)
+    int* rem;
+    int* minkey;       // [2][V*G]
+    int* cntI;
+    int* ovfseg;
+    unsigned int* thresh;
+    int* blockcnt;     // [ceil(V*n / SEL_BLOCK)]
+    // work lists (append-only over the whole run)
+    unsigned int* wl;
+    unsigned int* dl;
+    int* ctr;          // [CTR_COUNT]
+    unsigned long long* stats;  // [ST_COUNT]
+    // global scratch for stars larger than CAP_CTA: slot b = 3 * scratch_cap u64 for block b
+    uint64_t* scratch;
+    int scratch_cap;
+    long long* blocksum;  // scan scratch
+};
+
+}  // namespace rlap

@@ -1,0 +1,149 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI, via rlap_b200.ops) against the
+in-repo oracle's keyed mode on the same seeded inputs. Bit-exact: rows, columns and fp32 weights."""
+import numpy as np
+import pytest
+import torch
+
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu_graph(ei, w, n, gptr):
+    import rlap_b200
+    return rlap_b200.prepare(torch.from_numpy(ei).cuda(), None if w is None else torch.from_numpy(w).cuda(), n,
+                             graph_ptr=gptr)
+
+
+@pytest.mark.parametrize("weighted", [False, True])
+def test_ingest_matches_oracle(oracle_port, weighted):
+    rng = np.random.default_rng(0)
+    for name, ei, n, gptr, t in util.small_cases():
+        w = util.sym_weights(ei) if weighted else None
+        # shuffle the edge order and add duplicates + explicit zeros: the coalesced result must not change
+        E = ei.shape[1]
+        dup = rng.integers(0, E, size=E // 10)
+        both = np.concatenate([dup, dup + 0])  # keep symmetric: add each picked edge and its twin
+        rev = {(int(a), int(b)): k for k, (a, b) in enumerate(zip(ei[0], ei[1]))}
+        twin = np.array([rev[(int(ei[1, k]), int(ei[0, k]))] for k in dup])
+        extra = np.concatenate([dup, twin])
+        ei2 = np.concatenate([ei, ei[:, extra]], axis=1)
+        w2 = None if w is None else np.concatenate([w, w[extra]])
+        zero = ei[:, :5]
+        ei2 = np.concatenate([ei2, zero], axis=1)
+        w2 = np.concatenate([np.ones(ei2.shape[1] - 5, dtype=np.float32) if w2 is None else w2,
+                             np.zeros(5, dtype=np.float32)])
+        perm = rng.permutation(ei2.shape[1])
+        ei2, w2 = np.ascontiguousarray(ei2[:, perm]), np.ascontiguousarray(w2[perm])
+        optr, ocol, ow = oracle_port.ingest(ei2, w2, n)
+        g = _gpu_graph(ei2, w2, n, gptr)
+        assert g.nnz == ocol.shape[0], name
+        assert np.array_equal(g.ptr.cpu().numpy().astype(np.int64), optr), name
+        assert np.array_equal(g.col.cpu().numpy()[: g.nnz], ocol), name
+        assert np.array_equal(g.w.cpu().numpy()[: g.nnz], ow), name  # bit exact fp32 sums
+
+
+@pytest.mark.parametrize("o_v,o_n", util.COMBOS)
+@pytest.mark.parametrize("weighted", [False, True])
+def test_views_match_oracle_bit_exact(oracle_port, o_v, o_n, weighted):
+    import rlap_b200
+    for name, ei, n, gptr, t in util.small_cases():
+        w = util.sym_weights(ei) if weighted else None
+        optr, ocol, ow = oracle_port.ingest(ei, w, n)
+        g = _gpu_graph(ei, w, n, gptr)
+        V = 3
+        (row, col, wt), vp = rlap_b200.schur_views(g, t, o_v, o_n, num_views=V, seed=1234, view_base=5, dtype=None)
+        row, col, wt, vp = row.cpu().numpy(), col.cpu().numpy(), wt.cpu().numpy(), vp.numpy()
+        for v in range(V):
+            r0, c0, w0 = oracle_port.keyed_schur(optr, ocol, ow, t, o_v, o_n, seed=1234, view=5 + v, graph_ptr=gptr)
+            s, e = vp[v], vp[v + 1]
+            assert e - s == r0.shape[0], (name, v, e - s, r0.shape[0])
+            assert np.array_equal(row[s:e], r0), (name, v)
+            assert np.array_equal(col[s:e], c0), (name, v)
+            assert np.array_equal(wt[s:e].view(np.uint32), w0.view(np.uint32)), (name, v)
+
+
+@pytest.mark.parametrize("o_v", ["random", "degree", "coarsen"])
+def test_full_clique_is_exact_schur_complement(oracle_port, o_v):
+    """sampling replaced by full clique elimination == exact Schur complement (fp32, 1e-5 relative)"""
+    import rlap_b200
+    from rlap_b200 import graphs
+    n = 100
+    ei = graphs.barabasi_albert(n, 50, seed=1)
+    w = util.sym_weights(ei)
+    g = _gpu_graph(ei, w, n, None)
+    (row, col, wt), vp = rlap_b200.schur_views(g, 50, o_v, "asc", seed=7, full_clique=True, dtype=None)
+    row, col, wt = row.cpu().numpy(), col.cpu().numpy(), wt.cpu().numpy()
+    L0 = util.laplacian(ei[0], ei[1], w, n)
+    keep = np.unique(col)
+    assert keep.shape[0] == 50
+    Ls = util.laplacian(row, col, wt, n)[np.ix_(keep, keep)]
+    ex = util.exact_schur(L0, keep)
+    assert np.linalg.norm(Ls - ex) / np.linalg.norm(ex) < 1e-5
+    # and bit-exact against the oracle's full-clique mode
+    optr, ocol, ow = oracle_port.ingest(ei, w, n)
+    r0, c0, w0 = oracle_port.keyed_schur(optr, ocol, ow, 50, o_v, "asc", seed=7, flags=oracle_port.FLAG_FULL_CLIQUE)
+    assert np.array_equal(row, r0) and np.array_equal(col, c0)
+    assert np.array_equal(wt.view(np.uint32), w0.view(np.uint32))
+
+
+def test_reference_api_contract():
+    """the reference's own test (tests/test_rlap.py:23-65): dtype float64 and a symmetric
+    unweighted adjacency over exactly n - num_remove surviving nodes; plus the README call shape"""
+    import rlap_b200
+    from rlap_b200 import graphs
+    for seed in range(3):
+        ei = torch.from_numpy(graphs.barabasi_albert(100, 50, seed=seed))
+        for weights in (None, torch.ones((1, ei.shape[1]))):
+            out = rlap_b200.ops.approximate_cholesky(edge_index=ei, edge_weights=weights, num_nodes=100, num_remove=50,
+                                                     o_v="random", o_n="asc")
+            assert out.dtype == torch.double and out.device == ei.device and out.shape[1] == 3
+            A = torch.zeros(100, 100)
+            A[out[:, 0].long(), out[:, 1].long()] = 1
+            assert torch.equal(A, A.t())
+            assert torch.unique(out[:, :2]).numel() == 50
+    a = torch.randn(100, 100, dtype=torch.double)
+    assert torch.allclose(rlap_b200.ops.identity(a), a, atol=1e-8)
+
+
+def test_edge_cases(oracle_port):
+    import rlap_b200
+    from rlap_b200 import graphs
+    ei = graphs.barabasi_albert(60, 3, seed=4)
+    n = 64  # 4 isolated vertices at the end: they consume removal slots (A.3)
+    optr, ocol, ow = oracle_port.ingest(ei, None, n)
+    g = _gpu_graph(ei, None, n, None)
+    for t in (0, 1, 4, 63, 64, 1000):
+        for o_v in ("random", "degree", "coarsen"):
+            (row, col, wt), vp = rlap_b200.schur_views(g, t, o_v, "asc", seed=3, dtype=None)
+            r0, c0, w0 = oracle_port.keyed_schur(optr, ocol, ow, t, o_v, "asc", seed=3)
+            assert np.array_equal(row.cpu().numpy(), r0) and np.array_equal(col.cpu().numpy(), c0), (t, o_v)
+            assert np.array_equal(wt.cpu().numpy(), w0), (t, o_v)
+            if t == 0:  # t = 0 returns the coalesced input
+                assert row.shape[0] == ei.shape[1]
+            if t >= n - 1:
+                assert row.shape[0] == 0
+    # empty graph
+    g0 = rlap_b200.prepare(torch.zeros((2, 0), dtype=torch.long).cuda(), None, 5)
+    out, vp = rlap_b200.schur_views(g0, 2, "degree", "asc", seed=1)
+    assert out.shape == (0, 3)
+    # errors instead of exit(0)
+    bad = torch.tensor([[0, 1, 2], [1, 0, 0]]).cuda()
+    with pytest.raises(ValueError):
+        rlap_b200.prepare(bad, None, 3)              # asymmetric
+    with pytest.raises(ValueError):
+        rlap_b200.prepare(torch.tensor([[0, 5], [5, 0]]).cuda(), None, 3)   # id out of range
+    with pytest.raises(ValueError):
+        rlap_b200.prepare(torch.tensor([[1], [1]]).cuda(), None, 3)          # self loop
+
+
+def test_host_abi_matches_device_path(oracle_port):
+    """rlap_approximate_cholesky_host (HOST [E,3] f64 in/out) == device path == oracle"""
+    from rlap_b200 import graphs, ops
+    ei = graphs.sbm(2708, 7, 5278, seed=0)
+    info = util.edge_info(ei)
+    out = ops.approximate_cholesky_host(info, 2708, 812, "degree", "asc", seed=99)
+    optr, ocol, ow = oracle_port.ingest(ei, None, 2708)
+    r0, c0, w0 = oracle_port.keyed_schur(optr, ocol, ow, 812, "degree", "asc", seed=99, view=0)
+    assert out.dtype == np.float64 and out.shape == (r0.shape[0], 3)
+    assert np.array_equal(out[:, 0], r0) and np.array_equal(out[:, 1], c0) and np.array_equal(out[:, 2], w0.astype(np.float64))
