@@ -109,7 +109,7 @@ def prepare(edge_index: Tensor, edge_weights: Optional[Tensor], num_nodes: int,
 
 def schur_views(graph: Graph, num_remove, o_v: str, o_n: str, num_views: int = 1, seed: Optional[int] = None,
                 view_base: int = 0, full_clique: bool = False, shared_order: bool = False, dtype=torch.float64,
-                pool_cap: int = 0, return_stats: bool = False):
+                pool_cap: int = 0, scratch_cap: int = 0, return_stats: bool = False):
     """num_views independent randomized Schur-complement views of `graph`.
 
     Returns (edge_info, view_ptr): edge_info is [sum E'_v, 3] (row, col, weight) of `dtype`
@@ -126,13 +126,14 @@ def schur_views(graph: Graph, num_remove, o_v: str, o_n: str, num_views: int = 1
         seed = _next_seed()
     flags = (_native.FLAG_FULL_CLIQUE if full_clique else 0) | (_native.FLAG_SHARED_ORDER if shared_order else 0)
     V = int(num_views)
-    if pool_cap == 0 and full_clique:
-        pool_cap = 8 * graph.nnz + 4096
+    if full_clique:  # test mode: cliques instead of trees, multi-edges pile up until a vertex goes
+        pool_cap = pool_cap or 8 * graph.nnz + 4096
+        scratch_cap = scratch_cap or (1 << 18)
     with torch.cuda.device(dev):
         stream = _stream_ptr()
         while True:
             wsb = ctypes.c_size_t(0)
-            _native.check(L.rlap_schur_workspace_bytes(graph.n, graph.nnz, G, V, pool_cap, 0, ctypes.byref(wsb)),
+            _native.check(L.rlap_schur_workspace_bytes(graph.n, graph.nnz, G, V, pool_cap, scratch_cap, ctypes.byref(wsb)),
                           "schur_workspace_bytes")
             ws = torch.empty(wsb.value, dtype=torch.uint8, device=dev)
             rows = np.zeros(V, dtype=np.int64)
@@ -140,7 +141,7 @@ def schur_views(graph: Graph, num_remove, o_v: str, o_n: str, num_views: int = 1
             st = L.rlap_schur_eliminate(graph.n, graph.nnz, graph.ptr.data_ptr(), graph.col.data_ptr(),
                                         graph.w.data_ptr(), G, graph.graph_ptr.ctypes.data, nr.ctypes.data,
                                         _native.OV[o_v], _native.ON[o_n], seed & 0xFFFFFFFFFFFFFFFF, view_base, V, flags,
-                                        pool_cap, 0, ws.data_ptr(), wsb.value, rows.ctypes.data, stats.ctypes.data,
+                                        pool_cap, scratch_cap, ws.data_ptr(), wsb.value, rows.ctypes.data, stats.ctypes.data,
                                         stream)
             if st == _native.RLAP_ERR_POOL_OVERFLOW:
                 pool_cap = 2 * int(stats[6])
