@@ -87,7 +87,10 @@ int rlap_schur_eliminate(int64_t n, int64_t nnz, const int32_t* csr_ptr, const i
                          int64_t n_graphs, const int64_t* graph_ptr, const int64_t* num_remove, int o_v, int o_n,
                          uint64_t seed, int64_t view_base, int64_t n_views, int flags, int64_t pool_cap,
                          int64_t scratch_cap, void* workspace, size_t workspace_bytes, int64_t* view_rows,
-                         int64_t* stats /* HOST int64[8] or NULL: rounds, fills, pool_used_max, ... */, void* stream);
+                         int64_t* stats /* HOST int64[16] or NULL, see below */, void* stream);
+/* stats: [0] rounds, [1] fill edges, [2] max pool entries used by a view, [3] largest merged star,
+ * [4] raw adjacency entries read at elimination, [5] output rows, [6] pool_cap used,
+ * [7] elimination kernel time (us, CUDA events), [8] emission count pass time (us). */
 
 /* ---- emission (replaces the output assembly, preconditioner.cc:435-457 / 789-810 / 916-934) ------
  * Writes the rows of all views back to back, view after view, each view sorted by (col, row):

@@ -292,8 +292,14 @@ int rlap_schur_eliminate(int64_t n, int64_t nnz, const int32_t* csr_ptr, const i
     CK(cudaMemsetAsync(P.stats, 0, sizeof(unsigned long long) * ST_COUNT, stream));
     CK(launch_setup_graphs((int)n, (int)n_graphs, L.gptr_dev, L.nrem_dev, n_graphs > 1 ? L.gid_dev : nullptr, L.teff_dev,
                            stream));
+    // device-side timing of the two phases (read back with the counts; no extra synchronisation)
+    static thread_local cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    if (!ev[0]) for (int i = 0; i < 3; i++) CK(cudaEventCreate(&ev[i]));
+    CK(cudaEventRecord(ev[0], stream));
     CK(launch_eliminate(P, stream));
+    CK(cudaEventRecord(ev[1], stream));
     CK(launch_emit_count(P, L.total_dev, stream));
+    CK(cudaEventRecord(ev[2], stream));
     k_gather_view_ptr<<<(unsigned)((n_views + 1 + 127) / 128), 128, 0, stream>>>(P.outoff, n, n_views, L.viewptr_dev);
     CK(cudaGetLastError());
     std::vector<long long> vp((size_t)n_views + 1);
@@ -316,7 +322,11 @@ int rlap_schur_eliminate(int64_t n, int64_t nnz, const int32_t* csr_ptr, const i
         stats[4] = (int64_t)hstats[ST_RAW];
         stats[5] = vp[(size_t)n_views];
         stats[6] = L.pool_cap;
-        stats[7] = 0;
+        float ms_elim = 0.f, ms_count = 0.f;
+        cudaEventElapsedTime(&ms_elim, ev[0], ev[1]);
+        cudaEventElapsedTime(&ms_count, ev[1], ev[2]);
+        stats[7] = (int64_t)(ms_elim * 1000.0f);   // k_eliminate, microseconds
+        stats[8] = (int64_t)(ms_count * 1000.0f);  // emission count pass + scan, microseconds
     }
     {
         std::lock_guard<std::mutex> lk(g_layout_mutex);

@@ -28,10 +28,10 @@ __device__ __forceinline__ int graph_of(const SchurParams& P, int v) { return P.
 // key of the degree bucket queue (preconditioner.cc:125-246 restated): number of live
 // list entries, never below 1 once the vertex had an edge (DegreePQDec is a no-op at key 1), 0 for
 // vertices that were isolated from the start.
-__device__ __forceinline__ int key_eff(const SchurParams& P, size_t vb, int v) {
-    int d0 = __ldg(P.ptr + v + 1) - __ldg(P.ptr + v);
-    if (d0 == 0) return 0;
-    return max(ldcg_i32(P.live + vb + v), 1);
+// state byte: 0 kept (o_v = random, not eligible), 1 pending, 2 eliminated, 4 pending and isolated from the start
+__device__ __forceinline__ int key_eff(const SchurParams& P, size_t idx, uint8_t st) {
+    if (st == 4) return 0;
+    return max(ldcg_i32(P.live + idx), 1);
 }
 __device__ __forceinline__ int key_nbr(const SchurParams& P, size_t vb, int u) {  // u has an edge: deg0 > 0
     return max(ldcg_i32(P.live + vb + u), 1);
@@ -211,8 +211,11 @@ __device__ __forceinline__ void push_fill(const SchurParams& P, size_t vb, int4*
 }
 
 // Eliminate vertex v of `view` (A.2 clique sampling / A.4 coarsening / full clique), DESIGN.md §3.3.
+struct LocalStats { unsigned long long fills = 0, raw = 0; int maxstar = 0; };
+
 template <bool CTA>
-__device__ void eliminate_star(const SchurParams& P, const RoundCtx& rc, int view, int v, StarBuf sb, CtaScratch* cs) {
+__device__ void eliminate_star(const SchurParams& P, const RoundCtx& rc, int view, int v, StarBuf sb, CtaScratch* cs,
+                               LocalStats& ls) {
     const size_t vb = (size_t)view * (size_t)P.n;
     const int gs = g_size<CTA>(), r = g_rank<CTA>();
     const uint32_t view_id = P.view_base + (uint32_t)view;
@@ -327,15 +330,12 @@ __device__ void eliminate_star(const SchurParams& P, const RoundCtx& rc, int vie
             }
         }
         if (r == 0) {
-            atomicAdd(P.stats + ST_FILLS, (unsigned long long)(ovf ? 0 : nf));
-            atomicMax(P.stats + ST_MAXSTAR, (unsigned long long)L);
-            atomicAdd(P.stats + ST_RAW, (unsigned long long)lraw);
+            ls.fills += (unsigned long long)(ovf ? 0 : nf);
+            ls.maxstar = max(ls.maxstar, L);
+            ls.raw += (unsigned long long)lraw;
         }
     }
-    if (r == 0) {
-        P.state[vb + v] = 2;
-        if (P.o_v != 0) atomicSub(P.rem + (size_t)view * P.G + graph_of(P, v), 1);
-    }
+    if (r == 0) P.state[vb + v] = 2;
     g_sync<CTA>();
 }
 
@@ -371,7 +371,7 @@ __device__ __forceinline__ StarBuf scratch_buf(const SchurParams& P) {
 
 // process work-list items [start, end): one warp per item; big stars are deferred to the block phase
 __device__ void run_warp_items(const SchurParams& P, const RoundCtx& rc, uint64_t* smem, CtaScratch* cs, int start,
-                               int end) {
+                               int end, LocalStats& ls) {
     const int gw = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int nw = (int)((gridDim.x * blockDim.x) >> 5);
     const int lane = threadIdx.x & 31;
@@ -385,7 +385,7 @@ __device__ void run_warp_items(const SchurParams& P, const RoundCtx& rc, uint64_
         }
         int lv = ldcg_i32(P.live + idx);
         if (lv <= CAP_WARP) {
-            eliminate_star<false>(P, rc, view, v, sb, cs);
+            eliminate_star<false>(P, rc, view, v, sb, cs, ls);
         } else if (lane == 0) {
             int pos = rc.dl_base + atomicAdd(P.ctr + rc.dslot, 1);
             P.dl[pos] = idx;
@@ -396,11 +396,11 @@ __device__ void run_warp_items(const SchurParams& P, const RoundCtx& rc, uint64_
 // deferred items [start, end): one block per item in shared memory; stars beyond CAP_CTA go to the
 // NSLOT blocks that own a global scratch slot
 __device__ void run_block_items(const SchurParams& P, const RoundCtx& rc, uint64_t* smem, CtaScratch* cs, int start,
-                                int end) {
+                                int end, LocalStats& ls) {
     for (int it = start + (int)blockIdx.x; it < end; it += (int)gridDim.x) {
         unsigned int idx = __ldcg(P.dl + it);
         int view = (int)(idx / (unsigned)P.n), v = (int)(idx % (unsigned)P.n);
-        if (ldcg_i32(P.live + idx) <= CAP_CTA) eliminate_star<true>(P, rc, view, v, cta_buf(smem), cs);
+        if (ldcg_i32(P.live + idx) <= CAP_CTA) eliminate_star<true>(P, rc, view, v, cta_buf(smem), cs, ls);
         __syncthreads();
     }
     if ((int)blockIdx.x < NSLOT) {
@@ -410,7 +410,7 @@ __device__ void run_block_items(const SchurParams& P, const RoundCtx& rc, uint64
             if (ldcg_i32(P.live + idx) <= CAP_CTA) continue;
             if ((j++ % NSLOT) != (int)blockIdx.x) continue;
             int view = (int)(idx / (unsigned)P.n), v = (int)(idx % (unsigned)P.n);
-            eliminate_star<true>(P, rc, view, v, scratch_buf(P), cs);
+            eliminate_star<true>(P, rc, view, v, scratch_buf(P), cs, ls);
             __syncthreads();
         }
     }
@@ -441,7 +441,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
             P.rank[idx] = rk;
             P.state[idx] = rk < __ldg(P.teff + g) ? 1 : 0;
         } else {
-            P.state[idx] = 1;
+            P.state[idx] = (__ldg(P.ptr + v + 1) == __ldg(P.ptr + v)) ? 4 : 1;
             P.candround[idx] = -1;
         }
     }
@@ -462,24 +462,55 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
     int dl_start = 0;
     int rounds = 0;
     RoundCtx rc;
+    LocalStats ls;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const unsigned uVN = (unsigned)VN, un = (unsigned)P.n;
 
     if (random_order) {
         // dependency counters: pending lower-ranked eligible neighbours; roots seed the work list
         // (they count as appended in round -1, i.e. on counter slot 2)
-        for (long long idx = tid; idx < VN; idx += nthr) {
-            if (ldcg_u8(P.state + idx) != 1) continue;
-            int view = (int)(idx / P.n), v = (int)(idx % P.n);
-            size_t vb = (size_t)view * P.n;
-            int rv = ldcg_i32(P.rank + idx);
-            int c = 0;
-            for (int p = __ldg(P.ptr + v), e = __ldg(P.ptr + v + 1); p < e; p++) {
-                int u = __ldg(P.col + p);
-                if (ldcg_u8(P.state + vb + u) == 1 && ldcg_i32(P.rank + vb + u) < rv) c++;
+        for (unsigned base = (unsigned)(tid - lane); base < uVN; base += (unsigned)nthr) {
+            unsigned idx = base + lane;
+            bool elig = idx < uVN && ldcg_u8(P.state + idx) == 1;
+            int view = 0, v = 0, rv = 0, b = 0, e = 0;
+            if (elig) {
+                view = (int)(idx / un); v = (int)(idx % un);
+                rv = ldcg_i32(P.rank + idx);
+                b = __ldg(P.ptr + v); e = __ldg(P.ptr + v + 1);
             }
-            P.blk[idx] = c;
-            if (c == 0) {
-                int pos = atomicAdd(P.ctr + CTR_WCNT0 + 2, 1);
-                P.wl[pos] = (unsigned int)idx;
+            const bool longrow = elig && (e - b) > 64;
+            int c = 0;
+            if (elig && !longrow) {
+                size_t vb = (size_t)view * P.n;
+                for (int p = b; p < e; p++) {
+                    int u = __ldg(P.col + p);
+                    if (ldcg_u8(P.state + vb + u) == 1 && ldcg_i32(P.rank + vb + u) < rv) c++;
+                }
+            }
+            unsigned todo = __ballot_sync(RLAP_FULL_MASK, longrow);
+            while (todo) {  // hubs: the warp walks the row together
+                int k = __ffs(todo) - 1;
+                todo &= todo - 1;
+                int kb = __shfl_sync(RLAP_FULL_MASK, b, k), ke = __shfl_sync(RLAP_FULL_MASK, e, k);
+                int krv = __shfl_sync(RLAP_FULL_MASK, rv, k);
+                size_t kvb = (size_t)__shfl_sync(RLAP_FULL_MASK, view, k) * P.n;
+                int cc = 0;
+                for (int p = kb + lane; p < ke; p += 32) {
+                    int u = __ldg(P.col + p);
+                    if (ldcg_u8(P.state + kvb + u) == 1 && ldcg_i32(P.rank + kvb + u) < krv) cc++;
+                }
+                cc = __reduce_add_sync(RLAP_FULL_MASK, cc);
+                if (lane == k) c = cc;
+            }
+            if (elig) P.blk[idx] = c;
+            bool root = elig && c == 0;
+            unsigned rm = __ballot_sync(RLAP_FULL_MASK, root);
+            if (rm) {
+                int pos0 = 0;
+                if (lane == 0) pos0 = atomicAdd(P.ctr + CTR_WCNT0 + 2, __popc(rm));
+                pos0 = __shfl_sync(RLAP_FULL_MASK, pos0, 0);
+                if (root) P.wl[pos0 + __popc(rm & lt)] = idx;
             }
         }
         grid.sync();
@@ -490,12 +521,12 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
             if (tid == 0) { P.ctr[CTR_WCNT0 + (rounds + 1) % 3] = 0; P.ctr[CTR_DCNT0 + (rounds + 1) % 3] = 0; }
             rc.wl_base = wl_end; rc.wslot = CTR_WCNT0 + rounds % 3;
             rc.dl_base = dl_start; rc.dslot = CTR_DCNT0 + rounds % 3;
-            run_warp_items(P, rc, smem, &cs, wl_start, wl_end);
+            run_warp_items(P, rc, smem, &cs, wl_start, wl_end, ls);
             wl_start = wl_end;
             grid.sync();
             int dl_end = dl_start + ldcg_i32(P.ctr + rc.dslot);
             if (dl_end != dl_start) {
-                run_block_items(P, rc, smem, &cs, dl_start, dl_end);
+                run_block_items(P, rc, smem, &cs, dl_start, dl_end, ls);
                 dl_start = dl_end;
                 grid.sync();
             }
@@ -515,43 +546,103 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
                 P.ctr[CTR_WCNT0 + (rounds + 1) % 3] = 0; P.ctr[CTR_DCNT0 + (rounds + 1) % 3] = 0;
             }
             for (long long s = tid; s < VG; s += nthr) { mk_other[s] = 0x7fffffff; P.cntI[s] = 0; P.ovfseg[s] = 0; }
-            for (long long idx = tid; idx < VN; idx += nthr) {
-                if (ldcg_u8(P.state + idx) == 2) continue;
-                int view = (int)(idx / P.n), v = (int)(idx % P.n);
-                size_t seg = (size_t)view * P.G + graph_of(P, v);
-                if (ldcg_i32(P.rem + seg) <= 0) continue;
-                atomicMin(mk + seg, key_eff(P, (size_t)view * P.n, v));
-                P.ctr[CTR_ACTIVE0 + par] = 1;
+            {
+                int* smin = (int*)smem;  // the star buffers are idle during this phase
+                const bool use_smem = VG <= (long long)(3 * CAP_CTA * 2);
+                if (use_smem) {
+                    for (int q = threadIdx.x; q < (int)VG; q += blockDim.x) smin[q] = 0x7fffffff;
+                    __syncthreads();
+                }
+                bool any = false;
+                for (unsigned base = (unsigned)(tid - lane); base < uVN; base += (unsigned)nthr) {
+                    unsigned idx = base + lane;
+                    bool valid = false;
+                    int key = 0x7fffffff, seg = 0;
+                    if (idx < uVN) {
+                        uint8_t st = ldcg_u8(P.state + idx);
+                        if (st != 2) {
+                            int view = (int)(idx / un), v = (int)(idx % un);
+                            seg = view * P.G + graph_of(P, v);
+                            if (ldcg_i32(P.rem + seg) > 0) { valid = true; key = key_eff(P, idx, st); }
+                        }
+                    }
+                    unsigned vm = __ballot_sync(RLAP_FULL_MASK, valid);
+                    if (vm == 0) continue;
+                    any = true;
+                    int leader = __ffs(vm) - 1;
+                    int seg0 = __shfl_sync(RLAP_FULL_MASK, seg, leader);
+                    bool same = __all_sync(RLAP_FULL_MASK, !valid || seg == seg0);
+                    if (same) {
+                        int k = __reduce_min_sync(RLAP_FULL_MASK, key);
+                        if (lane == leader) { if (use_smem) atomicMin(smin + seg0, k); else atomicMin(mk + seg0, k); }
+                    } else if (valid) {
+                        if (use_smem) atomicMin(smin + seg, key); else atomicMin(mk + seg, key);
+                    }
+                }
+                if (use_smem) {
+                    __syncthreads();
+                    for (int q = threadIdx.x; q < (int)VG; q += blockDim.x) {
+                        int k = smin[q];
+                        if (k != 0x7fffffff) atomicMin(mk + q, k);
+                    }
+                    __syncthreads();
+                }
+                if (any && lane == 0) P.ctr[CTR_ACTIVE0 + par] = 1;
             }
             grid.sync();
             if (ldcg_i32(P.ctr + CTR_ACTIVE0 + par) == 0) break;
             // phase B: members of the minimum bucket with no bucket neighbour of higher id
-            for (long long idx = tid; idx < VN; idx += nthr) {
-                if (ldcg_u8(P.state + idx) == 2) continue;
-                int view = (int)(idx / P.n), v = (int)(idx % P.n);
-                size_t vb = (size_t)view * P.n;
-                size_t seg = (size_t)view * P.G + graph_of(P, v);
-                int rm = ldcg_i32(P.rem + seg);
-                if (rm <= 0) continue;
-                int m = ldcg_i32(mk + seg);
-                if (key_eff(P, vb, v) != m) continue;
-                bool ok = true;
-                for (int p = __ldg(P.ptr + v), e = __ldg(P.ptr + v + 1); p < e && ok; p++) {
-                    int u = __ldg(P.col + p);
-                    if (u > v && ldcg_u8(P.state + vb + u) != 2 && key_nbr(P, vb, u) == m) ok = false;
+            for (unsigned base = (unsigned)(tid - lane); base < uVN; base += (unsigned)nthr) {
+                unsigned idx = base + lane;
+                bool cand = false;
+                int seg = 0, rm = 0;
+                if (idx < uVN) {
+                    uint8_t st = ldcg_u8(P.state + idx);
+                    if (st != 2) {
+                        int view = (int)(idx / un), v = (int)(idx % un);
+                        size_t vb = (size_t)view * P.n;
+                        seg = view * P.G + graph_of(P, v);
+                        rm = ldcg_i32(P.rem + seg);
+                        if (rm > 0) {
+                            int m = ldcg_i32(mk + seg);
+                            if (key_eff(P, idx, st) == m) {
+                                bool ok = true;
+                                for (int p = __ldg(P.ptr + v), e = __ldg(P.ptr + v + 1); p < e && ok; p++) {
+                                    int u = __ldg(P.col + p);
+                                    if (u > v && ldcg_u8(P.state + vb + u) != 2 && key_nbr(P, vb, u) == m) ok = false;
+                                }
+                                const int4* pool = P.pool + (size_t)view * (size_t)P.pool_cap;
+                                for (int p = ldcg_i32(P.head + idx); p >= 0 && ok;) {
+                                    int4 en = __ldcg(pool + p);
+                                    if (en.x > v && ldcg_u8(P.state + vb + en.x) != 2 && key_nbr(P, vb, en.x) == m) ok = false;
+                                    p = en.z;
+                                }
+                                cand = ok;
+                            }
+                        }
+                    }
                 }
-                const int4* pool = P.pool + (size_t)view * (size_t)P.pool_cap;
-                for (int p = ldcg_i32(P.head + idx); p >= 0 && ok;) {
-                    int4 en = __ldcg(pool + p);
-                    if (en.x > v && ldcg_u8(P.state + vb + en.x) != 2 && key_nbr(P, vb, en.x) == m) ok = false;
-                    p = en.z;
+                unsigned cm = __ballot_sync(RLAP_FULL_MASK, cand);
+                if (cm == 0) continue;
+                int leader = __ffs(cm) - 1;
+                int pos0 = 0;
+                if (lane == leader) pos0 = atomicAdd(P.ctr + rc.wslot, __popc(cm));
+                pos0 = __shfl_sync(RLAP_FULL_MASK, pos0, leader);
+                int seg0 = __shfl_sync(RLAP_FULL_MASK, seg, leader);
+                bool same = __all_sync(RLAP_FULL_MASK, !cand || seg == seg0);
+                if (cand) {
+                    P.candround[idx] = rounds;
+                    P.wl[rc.wl_base + pos0 + __popc(cm & lt)] = idx;
                 }
-                if (!ok) continue;
-                P.candround[idx] = rounds;
-                int pos = rc.wl_base + atomicAdd(P.ctr + rc.wslot, 1);
-                P.wl[pos] = (unsigned int)idx;
-                int c = atomicAdd(P.cntI + seg, 1);
-                if (c + 1 > rm) P.ctr[CTR_OVF0 + par] = 1;
+                if (same) {
+                    if (lane == leader) {
+                        int c = atomicAdd(P.cntI + seg0, __popc(cm));
+                        if (c + __popc(cm) > rm) P.ctr[CTR_OVF0 + par] = 1;
+                    }
+                } else if (cand) {
+                    int c = atomicAdd(P.cntI + seg, 1);
+                    if (c + 1 > rm) P.ctr[CTR_OVF0 + par] = 1;
+                }
             }
             grid.sync();
             // phase C: a graph that selected more than it may still remove keeps its highest ids
@@ -624,14 +715,19 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
                 }
                 grid.sync();
             }
+            // the truncated count is what phase D will eliminate
+            for (long long q = tid; q < VG; q += nthr) {
+                int rm = ldcg_i32(P.rem + q), c = ldcg_i32(P.cntI + q);
+                if (c > 0) P.rem[q] = rm - min(rm, c);
+            }
             // phase D: eliminate
             int wl_end = wl_start + ldcg_i32(P.ctr + rc.wslot);
-            run_warp_items(P, rc, smem, &cs, wl_start, wl_end);
+            run_warp_items(P, rc, smem, &cs, wl_start, wl_end, ls);
             wl_start = wl_end;
             grid.sync();
             int dl_end = dl_start + ldcg_i32(P.ctr + rc.dslot);
             if (dl_end != dl_start) {
-                run_block_items(P, rc, smem, &cs, dl_start, dl_end);
+                run_block_items(P, rc, smem, &cs, dl_start, dl_end, ls);
                 dl_start = dl_end;
                 grid.sync();
             }
@@ -639,6 +735,11 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
         }
     }
     if (tid == 0) P.ctr[CTR_ROUNDS] = rounds;
+    if (ls.raw | ls.fills) {
+        atomicAdd(P.stats + ST_FILLS, ls.fills);
+        atomicAdd(P.stats + ST_RAW, ls.raw);
+        atomicMax(P.stats + ST_MAXSTAR, (unsigned long long)ls.maxstar);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -137,7 +137,7 @@ def schur_views(graph: Graph, num_remove, o_v: str, o_n: str, num_views: int = 1
                           "schur_workspace_bytes")
             ws = torch.empty(wsb.value, dtype=torch.uint8, device=dev)
             rows = np.zeros(V, dtype=np.int64)
-            stats = np.zeros(8, dtype=np.int64)
+            stats = np.zeros(16, dtype=np.int64)
             st = L.rlap_schur_eliminate(graph.n, graph.nnz, graph.ptr.data_ptr(), graph.col.data_ptr(),
                                         graph.w.data_ptr(), G, graph.graph_ptr.ctypes.data, nr.ctypes.data,
                                         _native.OV[o_v], _native.ON[o_n], seed & 0xFFFFFFFFFFFFFFFF, view_base, V, flags,
@@ -168,7 +168,8 @@ def schur_views(graph: Graph, num_remove, o_v: str, o_n: str, num_views: int = 1
             if dtype != torch.float64:
                 out = out.to(dtype)
     if return_stats:
-        names = ["rounds", "fills", "pool_used_max", "max_star", "raw_entries_read", "rows", "pool_cap", "_"]
+        names = ["rounds", "fills", "pool_used_max", "max_star", "raw_entries_read", "rows", "pool_cap", "elim_us",
+                 "emit_count_us"]
         return out, view_ptr, dict(zip(names, (int(x) for x in stats)))
     return out, view_ptr
 
