@@ -82,7 +82,7 @@ int rlap_ingest(const int64_t* src, const int64_t* dst, const float* w, int64_t 
  * After rlap_schur_eliminate returns, view_rows (HOST int64[n_views]) holds the number of output
  * rows of every view. Synchronises `stream` once. */
 int rlap_schur_workspace_bytes(int64_t n, int64_t nnz, int64_t n_graphs, int64_t n_views, int64_t pool_cap,
-                               int64_t scratch_cap, size_t* bytes);
+                               int64_t scratch_cap, int flags, size_t* bytes);
 int rlap_schur_eliminate(int64_t n, int64_t nnz, const int32_t* csr_ptr, const int32_t* csr_col, const float* csr_w,
                          int64_t n_graphs, const int64_t* graph_ptr, const int64_t* num_remove, int o_v, int o_n,
                          uint64_t seed, int64_t view_base, int64_t n_views, int flags, int64_t pool_cap,

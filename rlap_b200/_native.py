@@ -48,7 +48,7 @@ def lib():
     L.rlap_version.restype = ctypes.c_int
     L.rlap_ingest_workspace_bytes.argtypes = [i64, i64, ctypes.POINTER(sz)]
     L.rlap_ingest.argtypes = [P, P, P, i64, i64, P, P, P, ctypes.POINTER(i64), ctypes.c_int, P, sz, P]
-    L.rlap_schur_workspace_bytes.argtypes = [i64, i64, i64, i64, i64, i64, ctypes.POINTER(sz)]
+    L.rlap_schur_workspace_bytes.argtypes = [i64, i64, i64, i64, i64, i64, ctypes.c_int, ctypes.POINTER(sz)]
     L.rlap_schur_eliminate.argtypes = [i64, i64, P, P, P, i64, P, P, ctypes.c_int, ctypes.c_int, u64, i64, i64,
                                        ctypes.c_int, i64, i64, P, sz, P, P, P]
     L.rlap_schur_emit.argtypes = [i64, i64, P, P, P, i64, P, sz, P, P, P, P, P]

@@ -22,6 +22,7 @@ cudaError_t launch_setup_graphs(int n, int G, const int* gptr, const long long* 
 cudaError_t eliminate_grid(int* blocks_out);
 cudaError_t launch_eliminate(const SchurParams& P, cudaStream_t stream);
 cudaError_t launch_emit_count(const SchurParams& P, long long* total_dev, cudaStream_t stream);
+cudaError_t launch_rowid(int n, long long nnz, const int* ptr, int* rowid, cudaStream_t stream);
 cudaError_t launch_emit_write(const SchurParams& P, int* out_row, int* out_col, float* out_w, double* out_f64,
                               cudaStream_t stream);
 }  // namespace rlap
@@ -167,6 +168,7 @@ struct SchurLayout {
     int* teff_dev;
     long long* total_dev;
     long long* viewptr_dev;   // [V+1]
+    int* rowid_dev;
     long long G, V, pool_cap, scratch_cap;
 };
 
@@ -178,7 +180,7 @@ static long long default_scratch_cap(long long n) {
 }
 
 static SchurLayout schur_layout(long long n, long long nnz, long long G, long long V, long long pool_cap,
-                                long long scratch_cap, void* ws) {
+                                long long scratch_cap, bool full_clique, void* ws) {
     SchurLayout L;
     memset(&L, 0, sizeof(L));
     if (pool_cap <= 0) pool_cap = default_pool_cap(nnz);
@@ -207,6 +209,13 @@ static SchurLayout schur_layout(long long n, long long nnz, long long G, long lo
     P.candround = c.take<int>(VN);
     P.outcnt = c.take<int>(VN);
     P.outoff = c.take<long long>(VN + 1);
+    P.rawoff = c.take<long long>(VN + 1);
+    L.rowid_dev = c.take<int>((size_t)nnz + 1);
+    P.rowid = L.rowid_dev;
+    // live entries never exceed the input's outside full-clique mode; the full-clique
+    // test mode may keep every pool entry alive as well
+    P.raw_cap = (long long)V * (nnz + (full_clique ? pool_cap : 0)) + 1;
+    P.raw = c.take<uint64_t>((size_t)P.raw_cap);
     P.pool = c.take<int4>((size_t)V * (size_t)pool_cap);
     P.pool_cap = pool_cap;
     P.pool_cursor = c.take<unsigned long long>((size_t)V);
@@ -239,11 +248,11 @@ static int check_dims(int64_t n, int64_t nnz, int64_t G, int64_t V, int64_t pool
 }
 
 int rlap_schur_workspace_bytes(int64_t n, int64_t nnz, int64_t n_graphs, int64_t n_views, int64_t pool_cap,
-                               int64_t scratch_cap, size_t* bytes) {
+                               int64_t scratch_cap, int flags, size_t* bytes) {
     if (!bytes) return RLAP_ERR_INVALID_ARG;
     int st = check_dims(n, nnz, n_graphs, n_views, pool_cap, scratch_cap);
     if (st) return st;
-    *bytes = schur_layout(n, nnz, n_graphs, n_views, pool_cap, scratch_cap, nullptr).bytes;
+    *bytes = schur_layout(n, nnz, n_graphs, n_views, pool_cap, scratch_cap, (flags & RLAP_FLAG_FULL_CLIQUE) != 0, nullptr).bytes;
     return RLAP_OK;
 }
 
@@ -269,7 +278,7 @@ int rlap_schur_eliminate(int64_t n, int64_t nnz, const int32_t* csr_ptr, const i
     if (graph_ptr[0] != 0 || graph_ptr[n_graphs] != n) return RLAP_ERR_INVALID_ARG;
     for (int64_t g = 0; g < n_graphs; g++)
         if (graph_ptr[g + 1] < graph_ptr[g]) return RLAP_ERR_INVALID_ARG;
-    SchurLayout L = schur_layout(n, nnz, n_graphs, n_views, pool_cap, scratch_cap, workspace);
+    SchurLayout L = schur_layout(n, nnz, n_graphs, n_views, pool_cap, scratch_cap, (flags & RLAP_FLAG_FULL_CLIQUE) != 0, workspace);
     if (workspace_bytes < L.bytes) return RLAP_ERR_WORKSPACE;
     SchurParams& P = L.P;
     P.ptr = csr_ptr;
@@ -290,6 +299,7 @@ int rlap_schur_eliminate(int64_t n, int64_t nnz, const int32_t* csr_ptr, const i
     }
     CK(cudaMemsetAsync(P.ctr, 0, sizeof(int) * CTR_COUNT, stream));
     CK(cudaMemsetAsync(P.stats, 0, sizeof(unsigned long long) * ST_COUNT, stream));
+    CK(launch_rowid((int)n, nnz, csr_ptr, L.rowid_dev, stream));
     CK(launch_setup_graphs((int)n, (int)n_graphs, L.gptr_dev, L.nrem_dev, n_graphs > 1 ? L.gid_dev : nullptr, L.teff_dev,
                            stream));
     // device-side timing of the two phases (read back with the counts; no extra synchronisation)
@@ -422,7 +432,7 @@ int rlap_approximate_cholesky_host(const double* edge_info, int64_t e, int64_t n
     int64_t pool_cap = 0;
     size_t wsb2 = 0;
     for (int attempt = 0;; attempt++) {
-        st = rlap_schur_workspace_bytes(n, nnz, 1, 1, pool_cap, 0, &wsb2);
+        st = rlap_schur_workspace_bytes(n, nnz, 1, 1, pool_cap, 0, 0, &wsb2);
         if (st) return st;
         DevBuf ws2(s);
         CK(ws2.alloc(wsb2));

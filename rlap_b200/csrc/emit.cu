@@ -1,0 +1,282 @@
+// emit.cu — emission (A.5): surviving vertices, multi-edges merged, rows sorted by (col, row).
+// Replaces the output assembly of the reference (rlap/csrc/preconditioner.cc:435-457 / 789-810 /
+// 916-934: pop every remaining vertex, walk its list, sort, merge, push rows).
+//
+// No list walking here: the exact live count of every surviving vertex is known (the `live`
+// counters the elimination maintains), so the live entries are first regrouped owner-major by a
+// counting sort that streams the base CSR and the fill pool linearly:
+//   k_emit_prep     live counts of survivors            -> scan -> rawoff
+//   k_emit_scatter  base entries + pool entries, alive endpoints only -> raw[rawoff[owner] + cursor++]
+//   k_emit_sort_*   per survivor: sort its contiguous segment by neighbour, merge multi-edges in place
+//                   (<= 32 entries: warp shuffles in registers; <= 128: warp + smem; else thread block)
+//                                                       -> scan -> outoff
+//   k_emit_copy     compact copy into the caller's buffers (packed and/or [E',3] float64)
+#include "rlap_device.cuh"
+#include "schur.cuh"
+#include "scan.cuh"
+#include "star.cuh"
+
+namespace rlap {
+
+// rawcnt / cursor reuse two per-vertex arrays that are dead once the elimination kernel has returned
+__device__ __forceinline__ int* rawcnt_of(const SchurParams& P) { return P.blk; }
+__device__ __forceinline__ int* cursor_of(const SchurParams& P) { return P.candround; }
+
+__global__ void k_rowid(int n, long long nnz, const int* ptr, int* rowid) {
+    long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nnz) return;
+    int lo = 0, hi = n;  // last v with ptr[v] <= p
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (__ldg(ptr + mid) <= p) lo = mid; else hi = mid;
+    }
+    rowid[p] = lo;
+}
+
+__global__ void k_emit_prep(SchurParams P) {
+    const long long VN = (long long)P.V * P.n;
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= VN) return;
+    int c = (P.state[idx] != 2) ? P.live[idx] : 0;
+    rawcnt_of(P)[idx] = c;
+    cursor_of(P)[idx] = 0;
+}
+
+__device__ __forceinline__ void scatter_one(const SchurParams& P, size_t vb, int owner, int nbr, uint32_t wbits) {
+    if (P.state[vb + owner] == 2 || P.state[vb + nbr] == 2) return;
+    long long pos = P.rawoff[vb + owner] + atomicAdd(cursor_of(P) + vb + owner, 1);
+    if (pos < P.raw_cap) P.raw[pos] = ((uint64_t)(uint32_t)nbr << 32) | (uint64_t)wbits;
+    else set_status(P, 6);
+}
+
+// blockIdx.y = view; grid-stride over the base entries, then over the view's pool entries
+__global__ void __launch_bounds__(256) k_emit_scatter(SchurParams P) {
+    const int view = blockIdx.y;
+    const size_t vb = (size_t)view * (size_t)P.n;
+    const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x, nt = (long long)gridDim.x * blockDim.x;
+    for (long long p = t0; p < P.nnz; p += nt)
+        scatter_one(P, vb, __ldg(P.rowid + p), __ldg(P.col + p), __float_as_uint(__ldg(P.w + p)));
+    long long used = (long long)P.pool_cursor[view];
+    if (used > P.pool_cap) used = P.pool_cap;
+    const int4* pool = P.pool + (size_t)view * (size_t)P.pool_cap;
+    for (long long e = t0; e < used; e += nt) {
+        int4 en = pool[e];
+        if (en.w >= 0) scatter_one(P, vb, en.w, en.x, (uint32_t)en.y);
+    }
+}
+
+// sort + merge a staged star (shared memory or scratch) and write the merged entries back to the
+// start of the vertex's raw segment, neighbours ascending
+template <bool CTA>
+__device__ void emit_sort_staged(const SchurParams& P, size_t idx, StarBuf sb, CtaScratch* cs) {
+    const int gs = g_size<CTA>(), r = g_rank<CTA>(), lane = threadIdx.x & 31;
+    const int lraw = rawcnt_of(P)[idx];
+    const long long off = P.rawoff[idx];
+    if (lraw > sb.cap) {
+        if (r == 0) { set_status(P, 6); P.outcnt[idx] = 0; }
+        g_sync<CTA>();
+        return;
+    }
+    uint32_t wmaxb = 0;
+    for (int i = r; i < lraw; i += gs) {
+        uint64_t a = P.raw[off + i];
+        sb.A[i] = a;
+        wmaxb = max(wmaxb, (uint32_t)a);
+    }
+    wmaxb = g_max_u32<CTA>(wmaxb, cs);
+    g_sync<CTA>();
+    int P2 = 0;
+    const int shift = star_shift(__uint_as_float(wmaxb), lraw);
+    const int L = star_sort_merge<CTA>(sb, lraw, shift, cs, &P2);
+    int carry = 0;
+    for (int base = 0; base < lraw; base += gs) {
+        int i = base + r;
+        uint64_t a = (i < lraw) ? sb.A[i] : RLAP_PAD_A;
+        bool keep = (i < lraw) && !a_dead(a);
+        unsigned m = __ballot_sync(RLAP_FULL_MASK, keep);
+        int pos = __popc(m & ((1u << lane) - 1u));
+        if (CTA) {
+            int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+            __syncthreads();
+            if (lane == 0) cs->wsum[w] = (unsigned long long)__popc(m);
+            __syncthreads();
+            int add = 0, tot = 0;
+            for (int k = 0; k < nw; k++) { int c = (int)cs->wsum[k]; if (k < w) add += c; tot += c; }
+            pos += add + carry;
+            carry += tot;
+        } else {
+            pos += carry;
+            carry += __popc(m);
+        }
+        if (keep) P.raw[off + pos] = a;
+    }
+    if (r == 0) P.outcnt[idx] = L;
+    g_sync<CTA>();
+}
+
+__global__ void __launch_bounds__(BLOCK_THREADS, 2) k_emit_sort_warp(SchurParams P) {
+    extern __shared__ __align__(16) uint64_t smem[];
+    __shared__ CtaScratch cs;
+    const long long VN = (long long)P.V * P.n;
+    const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    StarBuf sb = warp_buf(smem);
+    for (long long base = gw * 32; base < VN; base += nw * 32) {
+        const long long idx = base + lane;
+        int lv = 0;
+        long long off = 0;
+        if (idx < VN) {
+            lv = rawcnt_of(P)[idx];
+            off = P.rawoff[idx];
+            if (lv == 0) P.outcnt[idx] = 0;
+        }
+        if (lv > CAP_WARP) {
+            int pos = atomicAdd(P.ctr + CTR_EMIT_DL, 1);
+            P.dl[pos] = (unsigned int)idx;
+        }
+        // register path: one vertex at a time, all 32 lanes on its (contiguous) segment
+        unsigned small = __ballot_sync(RLAP_FULL_MASK, lv > 0 && lv <= 32);
+        uint64_t a_next = RLAP_PAD_A;
+        if (small) {
+            int k = __ffs(small) - 1;
+            int klv = __shfl_sync(RLAP_FULL_MASK, lv, k);
+            long long koff = __shfl_sync(RLAP_FULL_MASK, off, k);
+            a_next = lane < klv ? P.raw[koff + lane] : RLAP_PAD_A;
+        }
+        while (small) {
+            const int k = __ffs(small) - 1;
+            small &= small - 1;
+            const long long koff = __shfl_sync(RLAP_FULL_MASK, off, k);
+            uint64_t a = a_next;
+            if (small) {  // prefetch the next vertex's segment while this one is sorted
+                int k2 = __ffs(small) - 1;
+                int klv2 = __shfl_sync(RLAP_FULL_MASK, lv, k2);
+                long long koff2 = __shfl_sync(RLAP_FULL_MASK, off, k2);
+                a_next = lane < klv2 ? P.raw[koff2 + lane] : RLAP_PAD_A;
+            }
+            a = warp_sort_u64(a);
+            unsigned long long q;
+            int shift;
+            unsigned hmask = warp_merge_sorted(a, q, shift, false);
+            if ((hmask >> lane) & 1u) P.raw[koff + __popc(hmask & lt)] = a;
+            if (lane == 0) P.outcnt[base + k] = __popc(hmask);
+        }
+        unsigned medium = __ballot_sync(RLAP_FULL_MASK, lv > 32 && lv <= CAP_WARP);
+        while (medium) {
+            const int k = __ffs(medium) - 1;
+            medium &= medium - 1;
+            emit_sort_staged<false>(P, (size_t)(base + k), sb, &cs);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(BLOCK_THREADS, 2) k_emit_sort_block(SchurParams P) {
+    extern __shared__ __align__(16) uint64_t smem[];
+    __shared__ CtaScratch cs;
+    const int end = P.ctr[CTR_EMIT_DL];
+    for (int it = (int)blockIdx.x; it < end; it += (int)gridDim.x) {
+        unsigned int idx = P.dl[it];
+        if (rawcnt_of(P)[idx] <= CAP_CTA) emit_sort_staged<true>(P, idx, cta_buf(smem), &cs);
+        __syncthreads();
+    }
+    if ((int)blockIdx.x < NSLOT) {
+        int j = 0;
+        for (int it = 0; it < end; it++) {
+            unsigned int idx = P.dl[it];
+            if (rawcnt_of(P)[idx] <= CAP_CTA) continue;
+            if ((j++ % NSLOT) != (int)blockIdx.x) continue;
+            emit_sort_staged<true>(P, idx, scratch_buf(P), &cs);
+            __syncthreads();
+        }
+    }
+}
+
+// compact copy: merged segment of every survivor -> final rows
+__global__ void __launch_bounds__(256) k_emit_copy(SchurParams P, int* out_row, int* out_col, float* out_w,
+                                                  double* out_f64) {
+    const long long VN = (long long)P.V * P.n;
+    const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    for (long long base = gw * 32; base < VN; base += nw * 32) {
+        const long long idx = base + lane;
+        int L = 0;
+        long long src = 0, dst = 0;
+        if (idx < VN) {
+            L = P.outcnt[idx];
+            src = P.rawoff[idx];
+            dst = P.outoff[idx];
+        }
+        unsigned todo = __ballot_sync(RLAP_FULL_MASK, L > 0);
+        while (todo) {
+            const int k = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int kL = __shfl_sync(RLAP_FULL_MASK, L, k);
+            const long long ksrc = __shfl_sync(RLAP_FULL_MASK, src, k), kdst = __shfl_sync(RLAP_FULL_MASK, dst, k);
+            const int v = (int)((base + k) % P.n);
+            for (int i = lane; i < kL; i += 32) {
+                uint64_t a = P.raw[ksrc + i];
+                long long o = kdst + i;
+                if (out_row) { out_row[o] = (int)a_nbr(a); out_col[o] = v; out_w[o] = a_w(a); }
+                if (out_f64) {
+                    out_f64[o * 3 + 0] = (double)a_nbr(a);
+                    out_f64[o * 3 + 1] = (double)v;
+                    out_f64[o * 3 + 2] = (double)a_w(a);
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-side launchers
+// ---------------------------------------------------------------------------------------------
+cudaError_t eliminate_grid(int* blocks_out);
+
+cudaError_t launch_rowid(int n, long long nnz, const int* ptr, int* rowid, cudaStream_t stream) {
+    if (nnz > 0) k_rowid<<<(unsigned)((nnz + 255) / 256), 256, 0, stream>>>(n, nnz, ptr, rowid);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_emit_count(const SchurParams& P, long long* total_dev, cudaStream_t stream) {
+    static bool attr_done = false;
+    const size_t smem = (size_t)3 * CAP_CTA * sizeof(uint64_t);
+    if (!attr_done) {
+        cudaFuncSetAttribute(k_emit_sort_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_emit_sort_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_done = true;
+    }
+    const long long VN = (long long)P.V * P.n;
+    cudaError_t e = cudaMemsetAsync(P.ctr + CTR_EMIT_DL, 0, sizeof(int), stream);
+    if (e != cudaSuccess) return e;
+    k_emit_prep<<<(unsigned)((VN + 255) / 256), 256, 0, stream>>>(P);
+    e = launch_exclusive_scan<long long>(P.blk, VN, P.rawoff, P.blocksum, nullptr, stream);
+    if (e != cudaSuccess) return e;
+    {
+        long long work = P.nnz > P.pool_cap ? P.nnz : P.pool_cap;
+        long long bx = (work + 256 * 4 - 1) / (256 * 4);
+        if (bx < 1) bx = 1;
+        if (bx > 148 * 8) bx = 148 * 8;
+        k_emit_scatter<<<dim3((unsigned)bx, (unsigned)P.V), 256, 0, stream>>>(P);
+    }
+    int blocks = 0;
+    e = eliminate_grid(&blocks);
+    if (e != cudaSuccess) return e;
+    k_emit_sort_warp<<<blocks, BLOCK_THREADS, smem, stream>>>(P);
+    k_emit_sort_block<<<blocks, BLOCK_THREADS, smem, stream>>>(P);
+    return launch_exclusive_scan<long long>(P.outcnt, VN, P.outoff, P.blocksum, total_dev, stream);
+}
+
+cudaError_t launch_emit_write(const SchurParams& P, int* out_row, int* out_col, float* out_w, double* out_f64,
+                              cudaStream_t stream) {
+    const long long VN = (long long)P.V * P.n;
+    long long bx = (VN + 255) / 256;  // one warp per 32 vertices
+    if (bx < 1) bx = 1;
+    if (bx > 148 * 16) bx = 148 * 16;
+    k_emit_copy<<<(unsigned)bx, 256, 0, stream>>>(P, out_row, out_col, out_w, out_f64);
+    return cudaGetLastError();
+}
+
+}  // namespace rlap

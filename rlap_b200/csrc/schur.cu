@@ -16,12 +16,11 @@
 #include "rlap_device.cuh"
 #include "schur.cuh"
 #include "scan.cuh"
+#include "star.cuh"
 
 namespace cg = cooperative_groups;
 
 namespace rlap {
-
-__device__ __forceinline__ void set_status(const SchurParams& P, int code) { atomicCAS(P.ctr + CTR_STATUS, 0, code); }
 
 __device__ __forceinline__ int graph_of(const SchurParams& P, int v) { return P.gid ? __ldg(P.gid + v) : 0; }
 
@@ -124,67 +123,6 @@ __device__ int star_gather(const SchurParams& P, int view, int v, StarBuf sb, Ct
     return cnt;
 }
 
-// Quantise, pad to a power of two, sort by neighbour and merge multi-edges in place: the first entry
-// of every run keeps the summed fixed-point weight (and, if the run has more than one entry, the
-// dequantised fp32 weight); the others are marked dead (weight word RLAP_DEAD_W, Q = 0) but keep the
-// neighbour id. Returns the number of distinct neighbours; *P2_out = padded length.
-template <bool CTA>
-__device__ int star_sort_merge(StarBuf sb, int lraw, int shift, CtaScratch* cs, int* P2_out) {
-    const int gs = g_size<CTA>(), r = g_rank<CTA>();
-    const int P2 = next_pow2(lraw);
-    for (int i = r; i < P2; i += gs) {
-        if (i < lraw) {
-            sb.Q[i] = quantize(a_w(sb.A[i]), shift);
-        } else {
-            sb.A[i] = RLAP_PAD_A;
-            sb.Q[i] = 0;
-        }
-        sb.K[i] = ~0ull;
-    }
-    g_sync<CTA>();
-    g_bitonic_sort<CTA, SORT_BY_A>(sb, P2);
-    int L = 0;
-    if (CTA) {
-        if (threadIdx.x == 0) cs->icount = 0;
-        __syncthreads();
-    }
-    const int lane = threadIdx.x & 31;
-    for (int base = 0; base < lraw; base += gs) {
-        int i = base + r;
-        bool act = i < lraw;
-        uint64_t a = act ? sb.A[i] : RLAP_PAD_A;
-        uint32_t nb = a_nbr(a);
-        bool headf = act && (i == 0 || a_nbr(sb.A[i - 1]) != nb);
-        unsigned long long qs = 0;
-        int c = 0;
-        if (headf) {
-            int j = i;
-            do { qs += sb.Q[j]; c++; j++; } while (j < lraw && a_nbr(sb.A[j]) == nb);
-        }
-        unsigned m = __ballot_sync(RLAP_FULL_MASK, headf);
-        g_sync<CTA>();  // every read of this chunk's runs is done before anything is rewritten
-        if (act) {
-            if (headf) {
-                sb.Q[i] = qs;
-                if (c > 1) sb.A[i] = ((uint64_t)nb << 32) | (uint64_t)__float_as_uint(dequantize(qs, shift));
-            } else {
-                sb.Q[i] = 0;
-                sb.A[i] = ((uint64_t)nb << 32) | (uint64_t)RLAP_DEAD_W;
-            }
-        }
-        if (CTA) {
-            if (lane == 0 && m) atomicAdd(&cs->icount, __popc(m));
-        } else {
-            L += __popc(m);
-        }
-    }
-    g_sync<CTA>();
-    if (CTA) L = cs->icount;
-    g_sync<CTA>();
-    *P2_out = P2;
-    return L;
-}
-
 __device__ __forceinline__ void push_entry(const SchurParams& P, size_t vb, int4* pool, int owner, int nbr, float w,
                                            int slot) {
     int4 en;
@@ -199,7 +137,11 @@ __device__ __forceinline__ void push_entry(const SchurParams& P, size_t vb, int4
 // fill edge (j,k,w): append to both endpoints; o_v = random also records the new dependency
 __device__ __forceinline__ void push_fill(const SchurParams& P, size_t vb, int4* pool, int j, int k, float w,
                                           long long slot) {
-    if (!(w > 0.f)) return;
+    if (!(w > 0.f)) {  // underflowed fill: leave two tombstones so that the pool can be read linearly
+        pool[slot] = make_int4(-1, 0, -1, -1);
+        pool[slot + 1] = make_int4(-1, 0, -1, -1);
+        return;
+    }
     push_entry(P, vb, pool, j, k, w, (int)slot);
     push_entry(P, vb, pool, k, j, w, (int)slot + 1);
     if (P.o_v == 0) {
@@ -337,32 +279,6 @@ __device__ void eliminate_star(const SchurParams& P, const RoundCtx& rc, int vie
     }
     if (r == 0) P.state[vb + v] = 2;
     g_sync<CTA>();
-}
-
-__device__ __forceinline__ StarBuf warp_buf(uint64_t* smem) {
-    int w = threadIdx.x >> 5;
-    StarBuf sb;
-    sb.A = smem + (size_t)w * 3 * CAP_WARP;
-    sb.Q = sb.A + CAP_WARP;
-    sb.K = sb.Q + CAP_WARP;
-    sb.cap = CAP_WARP;
-    return sb;
-}
-__device__ __forceinline__ StarBuf cta_buf(uint64_t* smem) {
-    StarBuf sb;
-    sb.A = smem;
-    sb.Q = smem + CAP_CTA;
-    sb.K = smem + 2 * CAP_CTA;
-    sb.cap = CAP_CTA;
-    return sb;
-}
-__device__ __forceinline__ StarBuf scratch_buf(const SchurParams& P) {
-    StarBuf sb;
-    sb.A = P.scratch + (size_t)blockIdx.x * 3 * (size_t)P.scratch_cap;
-    sb.Q = sb.A + P.scratch_cap;
-    sb.K = sb.Q + P.scratch_cap;
-    sb.cap = P.scratch_cap;
-    return sb;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -742,126 +658,6 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// emission (A.5): surviving vertices, multi-edges merged, neighbours ascending
-// ---------------------------------------------------------------------------------------------
-template <bool CTA, bool WRITE>
-__device__ void emit_star(const SchurParams& P, int view, int v, StarBuf sb, CtaScratch* cs, int* out_row, int* out_col,
-                          float* out_w, double* out_f64) {
-    const size_t vb = (size_t)view * (size_t)P.n;
-    const int gs = g_size<CTA>(), r = g_rank<CTA>();
-    uint32_t wmaxb;
-    int lraw = star_gather<CTA>(P, view, v, sb, cs, &wmaxb);
-    if (lraw > sb.cap) {
-        if (r == 0) { set_status(P, 6); if (!WRITE) P.outcnt[vb + v] = 0; }
-        g_sync<CTA>();
-        return;
-    }
-    int L = 0, P2 = 0;
-    if (lraw > 0) {
-        const int shift = star_shift(__uint_as_float(wmaxb), lraw);
-        L = star_sort_merge<CTA>(sb, lraw, shift, cs, &P2);
-    }
-    if (!WRITE) {
-        if (r == 0) P.outcnt[vb + v] = L;
-    } else if (L > 0) {
-        const long long off = P.outoff[vb + v];
-        const int lane = threadIdx.x & 31;
-        int carry = 0;
-        for (int base = 0; base < lraw; base += gs) {
-            int i = base + r;
-            uint64_t a = (i < lraw) ? sb.A[i] : RLAP_PAD_A;
-            bool live = (i < lraw) && !a_dead(a);
-            unsigned m = __ballot_sync(RLAP_FULL_MASK, live);
-            int pos = __popc(m & ((1u << lane) - 1u));
-            if (CTA) {
-                int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-                __syncthreads();
-                if (lane == 0) cs->wsum[w] = (unsigned long long)__popc(m);
-                __syncthreads();
-                int add = 0, tot = 0;
-                for (int k = 0; k < nw; k++) { int c = (int)cs->wsum[k]; if (k < w) add += c; tot += c; }
-                pos += add + carry;
-                carry += tot;
-            } else {
-                pos += carry;
-                carry += __popc(m);
-            }
-            if (live) {
-                long long o = off + pos;
-                if (out_row) { out_row[o] = (int)a_nbr(a); out_col[o] = v; out_w[o] = a_w(a); }
-                if (out_f64) {
-                    out_f64[o * 3 + 0] = (double)a_nbr(a);
-                    out_f64[o * 3 + 1] = (double)v;
-                    out_f64[o * 3 + 2] = (double)a_w(a);
-                }
-            }
-        }
-    }
-    g_sync<CTA>();
-}
-
-template <bool WRITE>
-__global__ void __launch_bounds__(BLOCK_THREADS, 2) k_emit_warp(SchurParams P, int* out_row, int* out_col, float* out_w,
-                                                               double* out_f64) {
-    extern __shared__ __align__(16) uint64_t smem[];
-    __shared__ CtaScratch cs;
-    const long long VN = (long long)P.V * P.n;
-    const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    StarBuf sb = warp_buf(smem);
-    // a warp takes 32 consecutive vertices, keeps the ones that have rows and serves them one by one
-    for (long long base = gw * 32; base < VN; base += nw * 32) {
-        long long idx = base + lane;
-        int lv = 0;
-        bool alive = false;
-        if (idx < VN) {
-            alive = P.state[idx] != 2;
-            lv = alive ? P.live[idx] : 0;
-            if (!WRITE && !(alive && lv > 0)) P.outcnt[idx] = 0;
-            if (WRITE && alive && lv > 0 && P.outcnt[idx] == 0) lv = 0;
-        }
-        bool big = lv > CAP_WARP;
-        if (!WRITE && big) {
-            int pos = atomicAdd(P.ctr + CTR_EMIT_DL, 1);
-            P.dl[pos] = (unsigned int)idx;
-        }
-        unsigned todo = __ballot_sync(RLAP_FULL_MASK, lv > 0 && !big);
-        while (todo) {
-            int k = __ffs(todo) - 1;
-            todo &= todo - 1;
-            long long id2 = base + k;
-            emit_star<false, WRITE>(P, (int)(id2 / P.n), (int)(id2 % P.n), sb, &cs, out_row, out_col, out_w, out_f64);
-        }
-    }
-}
-
-template <bool WRITE>
-__global__ void __launch_bounds__(BLOCK_THREADS, 2) k_emit_block(SchurParams P, int* out_row, int* out_col, float* out_w,
-                                                                double* out_f64) {
-    extern __shared__ __align__(16) uint64_t smem[];
-    __shared__ CtaScratch cs;
-    int end = P.ctr[CTR_EMIT_DL];
-    for (int it = (int)blockIdx.x; it < end; it += (int)gridDim.x) {
-        unsigned int idx = P.dl[it];
-        int view = (int)(idx / (unsigned)P.n), v = (int)(idx % (unsigned)P.n);
-        if (P.live[idx] <= CAP_CTA) emit_star<true, WRITE>(P, view, v, cta_buf(smem), &cs, out_row, out_col, out_w, out_f64);
-        __syncthreads();
-    }
-    if ((int)blockIdx.x < NSLOT) {
-        int j = 0;
-        for (int it = 0; it < end; it++) {
-            unsigned int idx = P.dl[it];
-            if (P.live[idx] <= CAP_CTA) continue;
-            if ((j++ % NSLOT) != (int)blockIdx.x) continue;
-            int view = (int)(idx / (unsigned)P.n), v = (int)(idx % (unsigned)P.n);
-            emit_star<true, WRITE>(P, view, v, scratch_buf(P), &cs, out_row, out_col, out_w, out_f64);
-            __syncthreads();
-        }
-    }
-}
-
 // gid[v] = graph of vertex v, teff[g] = min(max(num_remove, 0), n_g - 1)
 __global__ void k_setup_graphs(int n, int G, const int* gptr, const long long* num_remove, int* gid, int* teff) {
     long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -921,40 +717,6 @@ cudaError_t launch_eliminate(const SchurParams& P, cudaStream_t stream) {
     SchurParams Pc = P;
     void* args[] = {(void*)&Pc};
     return cudaLaunchCooperativeKernel((void*)k_eliminate, dim3(blocks), dim3(BLOCK_THREADS), args, kSmemBytes, stream);
-}
-
-template <bool WRITE>
-static cudaError_t launch_emit_pass(const SchurParams& P, int* out_row, int* out_col, float* out_w, double* out_f64,
-                                    cudaStream_t stream) {
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(k_emit_warp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
-        cudaFuncSetAttribute(k_emit_warp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
-        cudaFuncSetAttribute(k_emit_block<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
-        cudaFuncSetAttribute(k_emit_block<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
-        attr_done = true;
-    }
-    int blocks = 0;
-    cudaError_t e = eliminate_grid(&blocks);  // same block shape: reuse the resident-grid size
-    if (e != cudaSuccess) return e;
-    k_emit_warp<WRITE><<<blocks, BLOCK_THREADS, kSmemBytes, stream>>>(P, out_row, out_col, out_w, out_f64);
-    k_emit_block<WRITE><<<blocks, BLOCK_THREADS, kSmemBytes, stream>>>(P, out_row, out_col, out_w, out_f64);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_emit_count(const SchurParams& P, long long* total_dev, cudaStream_t stream) {
-    // the deferred list is reused: reset its tail first
-    cudaError_t e = cudaMemsetAsync(P.ctr + CTR_EMIT_DL, 0, sizeof(int), stream);
-    if (e != cudaSuccess) return e;
-    e = launch_emit_pass<false>(P, nullptr, nullptr, nullptr, nullptr, stream);
-    if (e != cudaSuccess) return e;
-    long long VN = (long long)P.V * P.n;
-    return launch_exclusive_scan<long long>(P.outcnt, VN, P.outoff, P.blocksum, total_dev, stream);
-}
-
-cudaError_t launch_emit_write(const SchurParams& P, int* out_row, int* out_col, float* out_w, double* out_f64,
-                              cudaStream_t stream) {
-    return launch_emit_pass<true>(P, out_row, out_col, out_w, out_f64, stream);
 }
 
 }  // namespace rlap

@@ -66,6 +66,11 @@ struct SchurParams {
     int* candround;    // degree / coarsen: last round in which the vertex was selected
     int* outcnt;       // emission: merged row count
     long long* outoff; // emission: [V*n + 1] exclusive prefix of outcnt
+    // emission staging: the live entries of every surviving vertex, owner-major, contiguous
+    const int* rowid;  // [nnz] owner of a CSR entry (graph level)
+    long long* rawoff; // [V*n + 1] exclusive prefix of the live counts of surviving vertices
+    uint64_t* raw;     // [raw_cap] (nbr << 32) | weight bits
+    long long raw_cap;
     // fill-entry pool: pool[view * pool_cap + p] = {nbr, weight bits, next, owner}
     int4* pool;
     long long pool_cap;

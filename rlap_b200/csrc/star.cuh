@@ -1,0 +1,164 @@
+// star.cuh — star staging shared by the elimination and emission kernels: shared-memory buffers,
+// sort + multi-edge merge of a staged star, and the register-resident (warp shuffle) variants used
+// for stars of at most 32 entries.
+#pragma once
+#include "rlap_device.cuh"
+#include "schur.cuh"
+
+namespace rlap {
+
+__device__ __forceinline__ void set_status(const SchurParams& P, int code) { atomicCAS(P.ctr + CTR_STATUS, 0, code); }
+
+__device__ __forceinline__ StarBuf warp_buf(uint64_t* smem) {
+    int w = threadIdx.x >> 5;
+    StarBuf sb;
+    sb.A = smem + (size_t)w * 3 * CAP_WARP;
+    sb.Q = sb.A + CAP_WARP;
+    sb.K = sb.Q + CAP_WARP;
+    sb.cap = CAP_WARP;
+    return sb;
+}
+__device__ __forceinline__ StarBuf cta_buf(uint64_t* smem) {
+    StarBuf sb;
+    sb.A = smem;
+    sb.Q = smem + CAP_CTA;
+    sb.K = smem + 2 * CAP_CTA;
+    sb.cap = CAP_CTA;
+    return sb;
+}
+__device__ __forceinline__ StarBuf scratch_buf(const SchurParams& P) {
+    StarBuf sb;
+    sb.A = P.scratch + (size_t)blockIdx.x * 3 * (size_t)P.scratch_cap;
+    sb.Q = sb.A + P.scratch_cap;
+    sb.K = sb.Q + P.scratch_cap;
+    sb.cap = P.scratch_cap;
+    return sb;
+}
+
+// Quantise, pad to a power of two, sort by neighbour and merge multi-edges in place: the first entry
+// of every run keeps the summed fixed-point weight (and, if the run has more than one entry, the
+// dequantised fp32 weight); the others are marked dead (weight word RLAP_DEAD_W, Q = 0) but keep the
+// neighbour id. Returns the number of distinct neighbours; *P2_out = padded length.
+template <bool CTA>
+__device__ int star_sort_merge(StarBuf sb, int lraw, int shift, CtaScratch* cs, int* P2_out) {
+    const int gs = g_size<CTA>(), r = g_rank<CTA>();
+    const int P2 = next_pow2(lraw);
+    for (int i = r; i < P2; i += gs) {
+        if (i < lraw) {
+            sb.Q[i] = quantize(a_w(sb.A[i]), shift);
+        } else {
+            sb.A[i] = RLAP_PAD_A;
+            sb.Q[i] = 0;
+        }
+        sb.K[i] = ~0ull;
+    }
+    g_sync<CTA>();
+    g_bitonic_sort<CTA, SORT_BY_A>(sb, P2);
+    int L = 0;
+    if (CTA) {
+        if (threadIdx.x == 0) cs->icount = 0;
+        __syncthreads();
+    }
+    const int lane = threadIdx.x & 31;
+    for (int base = 0; base < lraw; base += gs) {
+        int i = base + r;
+        bool act = i < lraw;
+        uint64_t a = act ? sb.A[i] : RLAP_PAD_A;
+        uint32_t nb = a_nbr(a);
+        bool headf = act && (i == 0 || a_nbr(sb.A[i - 1]) != nb);
+        unsigned long long qs = 0;
+        int c = 0;
+        if (headf) {
+            int j = i;
+            do { qs += sb.Q[j]; c++; j++; } while (j < lraw && a_nbr(sb.A[j]) == nb);
+        }
+        unsigned m = __ballot_sync(RLAP_FULL_MASK, headf);
+        g_sync<CTA>();  // every read of this chunk's runs is done before anything is rewritten
+        if (act) {
+            if (headf) {
+                sb.Q[i] = qs;
+                if (c > 1) sb.A[i] = ((uint64_t)nb << 32) | (uint64_t)__float_as_uint(dequantize(qs, shift));
+            } else {
+                sb.Q[i] = 0;
+                sb.A[i] = ((uint64_t)nb << 32) | (uint64_t)RLAP_DEAD_W;
+            }
+        }
+        if (CTA) {
+            if (lane == 0 && m) atomicAdd(&cs->icount, __popc(m));
+        } else {
+            L += __popc(m);
+        }
+    }
+    g_sync<CTA>();
+    if (CTA) L = cs->icount;
+    g_sync<CTA>();
+    *P2_out = P2;
+    return L;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// register-resident stars: one entry per lane
+// ---------------------------------------------------------------------------------------------
+
+// ascending bitonic sort of one 64-bit key per lane across the warp
+__device__ __forceinline__ uint64_t warp_sort_u64(uint64_t a) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            uint64_t o = __shfl_xor_sync(RLAP_FULL_MASK, a, j);
+            bool take_min = (((lane & j) == 0) == ((lane & k) == 0));
+            bool lt = a < o;
+            a = (take_min == lt) ? a : o;
+        }
+    }
+    return a;
+}
+
+// Merge the runs of equal neighbour of a SORTED register star (a = PAD beyond the entries).
+// On return: head lanes hold the merged entry (a with the merged fp32 weight, *q = summed fixed-point
+// weight), the other entries are marked dead (weight word RLAP_DEAD_W, *q = 0). Returns the head mask.
+// need_q: compute *q even when the star has no multi-edge (the elimination needs it, the emission does not).
+__device__ __forceinline__ unsigned warp_merge_sorted(uint64_t& a, unsigned long long& q, int& shift, bool need_q) {
+    const int lane = threadIdx.x & 31;
+    const bool valid = a != RLAP_PAD_A;
+    const uint32_t nb = a_nbr(a);
+    const uint32_t pnb = __shfl_up_sync(RLAP_FULL_MASK, nb, 1);
+    const bool head = valid && (lane == 0 || pnb != nb);
+    const unsigned vmask = __ballot_sync(RLAP_FULL_MASK, valid);
+    const unsigned hmask = __ballot_sync(RLAP_FULL_MASK, head);
+    q = 0;
+    shift = 0;
+    if (vmask == 0) return 0;
+    const bool dups = hmask != vmask;
+    if (dups || need_q) {
+        uint32_t wb = valid ? (uint32_t)a : 0u;
+        uint32_t wmaxb = warp_max_u32(wb);
+        shift = star_shift(__uint_as_float(wmaxb), __popc(vmask));
+        q = valid ? quantize(a_w(a), shift) : 0ull;
+    }
+    if (dups) {
+        unsigned long long qs = q;
+        int cnt = valid ? 1 : 0;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            unsigned long long oq = __shfl_down_sync(RLAP_FULL_MASK, qs, d);
+            int oc = __shfl_down_sync(RLAP_FULL_MASK, cnt, d);
+            uint32_t onb = __shfl_down_sync(RLAP_FULL_MASK, nb, d);
+            bool ov = (vmask >> ((lane + d) & 31)) & 1u;
+            if (valid && lane + d < 32 && ov && onb == nb) { qs += oq; cnt += oc; }
+        }
+        if (head) {
+            q = qs;
+            if (cnt > 1) a = ((uint64_t)nb << 32) | (uint64_t)__float_as_uint(dequantize(qs, shift));
+        } else if (valid) {
+            q = 0;
+            a = ((uint64_t)nb << 32) | (uint64_t)RLAP_DEAD_W;
+        }
+    }
+    return hmask;
+}
+
+}  // namespace rlap

@@ -133,7 +133,7 @@ def schur_views(graph: Graph, num_remove, o_v: str, o_n: str, num_views: int = 1
         stream = _stream_ptr()
         while True:
             wsb = ctypes.c_size_t(0)
-            _native.check(L.rlap_schur_workspace_bytes(graph.n, graph.nnz, G, V, pool_cap, scratch_cap, ctypes.byref(wsb)),
+            _native.check(L.rlap_schur_workspace_bytes(graph.n, graph.nnz, G, V, pool_cap, scratch_cap, flags, ctypes.byref(wsb)),
                           "schur_workspace_bytes")
             ws = torch.empty(wsb.value, dtype=torch.uint8, device=dev)
             rows = np.zeros(V, dtype=np.int64)

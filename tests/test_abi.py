@@ -49,11 +49,11 @@ def test_workspace_queries_validate_arguments():
     b = ctypes.c_size_t(0)
     assert L.rlap_ingest_workspace_bytes(1000, 5000, ctypes.byref(b)) == 0 and b.value > 5000 * 8
     assert L.rlap_ingest_workspace_bytes(-1, 5, ctypes.byref(b)) == 1
-    assert L.rlap_schur_workspace_bytes(1000, 5000, 1, 4, 0, 0, ctypes.byref(b)) == 0
+    assert L.rlap_schur_workspace_bytes(1000, 5000, 1, 4, 0, 0, 0, ctypes.byref(b)) == 0
     one = b.value
-    assert L.rlap_schur_workspace_bytes(1000, 5000, 1, 8, 0, 0, ctypes.byref(b)) == 0 and b.value > one
-    assert L.rlap_schur_workspace_bytes(1000, 5000, 0, 4, 0, 0, ctypes.byref(b)) == 1
-    assert L.rlap_schur_workspace_bytes(1 << 29, 5000, 1, 4, 0, 0, ctypes.byref(b)) == 1   # V*n too large
+    assert L.rlap_schur_workspace_bytes(1000, 5000, 1, 8, 0, 0, 0, ctypes.byref(b)) == 0 and b.value > one
+    assert L.rlap_schur_workspace_bytes(1000, 5000, 0, 4, 0, 0, 0, ctypes.byref(b)) == 1
+    assert L.rlap_schur_workspace_bytes(1 << 29, 5000, 1, 4, 0, 0, 0, ctypes.byref(b)) == 1   # V*n too large
 
 
 def test_no_cpu_fallback():
