@@ -256,7 +256,7 @@ __device__ void eliminate_star(const SchurParams& P, const RoundCtx& rc, int vie
         // every push (and, for o_v = random, every dependency increment) is ordered before the
         // decrements below: a neighbour's counter can only reach zero once all its lower-ranked
         // eventual neighbours are gone
-        __threadfence();
+        if (P.o_v == 0) __threadfence();
         g_sync<CTA>();
         for (int i = r; i < P2; i += gs) {
             uint64_t a = sb.A[i];
@@ -281,30 +281,225 @@ __device__ void eliminate_star(const SchurParams& P, const RoundCtx& rc, int vie
     g_sync<CTA>();
 }
 
+// Register-resident elimination: a tile of W lanes (8, 16 or 32) holds one star, one entry per lane, and
+// the 32 / W tiles of a warp run in lock step (all shuffles are tile-wide). `idx` is the tile's work
+// item (uniform inside the tile) or 0xffffffff for an idle tile. Returns true for the lanes of a tile
+// whose star did not fit (raw list, dead entries included, longer than W): nothing was done for it and
+// the caller retries on a wider tile or the shared-memory path. Same arithmetic, same result.
+template <int W>
+__device__ bool eliminate_star_tile(const SchurParams& P, const RoundCtx& rc, unsigned int idx, LocalStats& ls) {
+    typedef Tile<W> T;
+    const int tl = T::tl();
+    const bool active = idx != 0xffffffffu;
+    const int view = active ? (int)(idx / (unsigned)P.n) : 0, v = active ? (int)(idx % (unsigned)P.n) : 0;
+    const size_t vb = (size_t)view * (size_t)P.n;
+    const uint32_t view_id = P.view_base + (uint32_t)view;
+    int4* pool = P.pool + (size_t)view * (size_t)P.pool_cap;
+    bool fail = false;
+    uint64_t a = RLAP_PAD_A;
+    if (active) {
+        const int b = __ldg(P.ptr + v), nb = __ldg(P.ptr + v + 1) - b;
+        if (nb > W) {
+            fail = true;
+        } else {
+            if (tl < nb) a = pack_a((uint32_t)__ldg(P.col + b + tl), __ldg(P.w + b + tl));
+            int slot = nb;
+            int p = ldcg_i32(P.head + vb + v);
+            while (p >= 0 && slot < W) {
+                int4 en = __ldcg(pool + p);
+                if (tl == slot) a = pack_a((uint32_t)en.x, __int_as_float(en.y));
+                slot++;
+                p = en.z;
+            }
+            if (p >= 0) fail = true;
+        }
+        if (fail) a = RLAP_PAD_A;
+        else if (a != RLAP_PAD_A && ldcg_u8(P.state + vb + a_nbr(a)) == 2) a = RLAP_PAD_A;
+    }
+    __syncwarp();
+    const bool go = active && !fail;
+    a = T::sort_u64(a);
+    const bool rawvalid = a != RLAP_PAD_A;         // raw live entry (multi-edge duplicates included)
+    const int rawnbr = (int)a_nbr(a);
+    const int lraw = __popc(T::ballot(rawvalid));
+    unsigned long long q;
+    int shift;
+    const unsigned hmask = T::merge_sorted(a, q, shift, true);
+    const int L = __popc(hmask);
+    const bool live = (hmask >> tl) & 1u;
+    const bool full = (P.flags & 1) != 0;
+    const bool coarsen = (P.o_v == 2) && !full;
+    const int on = coarsen ? 2 : P.o_n;
+    uint64_t key = ~0ull;
+    if (live) {
+        if (full || on == 0) key = q;
+        else if (on == 1) key = ~q;
+        else {
+            uint4 x = philox4x32_10(P.k0, P.k1, (uint32_t)v, a_nbr(a), view_id, TAG_STAR);
+            key = ((uint64_t)x.z << 32) | (uint64_t)x.w;
+        }
+    } else {
+        a = RLAP_PAD_A;
+        q = 0;
+    }
+    T::sort_kaq(key, a, q);
+    const unsigned long long C = T::incl_scan(q);
+    const unsigned long long S = __shfl_sync(RLAP_FULL_MASK, C, (L > 0 ? L - 1 : 0), W);
+    const long long nf = (L < 1) ? 0 : (full ? (long long)L * (L - 1) / 2 : (long long)(L - 1));
+    long long slot0 = 0;
+    {
+        unsigned long long s0 = 0;
+        if (go && tl == 0 && nf > 0) s0 = atomicAdd(P.pool_cursor + view, (unsigned long long)(2 * nf));
+        slot0 = (long long)__shfl_sync(RLAP_FULL_MASK, s0, 0, W);
+    }
+    const bool ovf = nf > 0 && slot0 + 2 * nf > P.pool_cap;
+    if (go && ovf && tl == 0) set_status(P, 5);
+    const bool emit = go && nf > 0 && !ovf;
+    if (full) {
+        const double Sf = __dmul_rn(__ull2double_rn(S), pow2d(-shift));
+        for (int b2 = 1; b2 < W; b2++) {
+            const uint64_t eb = __shfl_sync(RLAP_FULL_MASK, a, b2, W);
+            if (emit && b2 < L && tl < b2) {
+                float w = __double2float_rn(__ddiv_rn(__dmul_rn((double)a_w(a), (double)a_w(eb)), Sf));
+                long long off = (long long)tl * (2LL * L - tl - 1) / 2;
+                push_fill(P, vb, pool, (int)a_nbr(a), (int)a_nbr(eb), w, slot0 + 2 * (off + (b2 - tl - 1)));
+            }
+        }
+    } else if (coarsen) {
+        uint4 x = philox4x32_10(P.k0, P.k1, (uint32_t)v, 0xffffffffu, view_id, TAG_PICK);
+        unsigned long long u = ((unsigned long long)x.x << 32) | (unsigned long long)x.y;
+        int koff = T::upper_bound(C, L, __umul64hi(u, S));
+        if (koff >= L) koff = L - 1;
+        if (koff < 0) koff = 0;
+        const uint64_t ek = __shfl_sync(RLAP_FULL_MASK, a, koff, W);
+        if (emit && tl < L && tl != koff) {
+            const double wk = (double)a_w(ek), wm = (double)a_w(a);
+            float w = __double2float_rn(__ddiv_rn(__dmul_rn(wk, wm), __dadd_rn(wk, wm)));
+            int sl = tl < koff ? tl : tl - 1;
+            push_fill(P, vb, pool, (int)a_nbr(a), (int)a_nbr(ek), w, slot0 + 2LL * sl);
+        }
+    } else {
+        const bool act = tl < L - 1;
+        unsigned long long rr = 0, rem = 0;
+        if (act) {
+            rem = S - C;
+            uint4 x = philox4x32_10(P.k0, P.k1, (uint32_t)v, a_nbr(a), view_id, TAG_STAR);
+            unsigned long long u = ((unsigned long long)x.x << 32) | (unsigned long long)x.y;
+            rr = C + __umul64hi(u, rem);
+        }
+        int koff = T::upper_bound(C, L, rr);
+        if (koff >= L) koff = L - 1;
+        if (koff < 0) koff = 0;
+        const uint64_t ek = __shfl_sync(RLAP_FULL_MASK, a, koff, W);
+        if (emit && act) {
+            float w = __double2float_rn(__ddiv_rn(__dmul_rn((double)a_w(a), __ull2double_rn(rem)), __ull2double_rn(S)));
+            push_fill(P, vb, pool, (int)a_nbr(a), (int)a_nbr(ek), w, slot0 + 2LL * tl);
+        }
+    }
+    // o_v = random: pushes and dependency increments are ordered before the decrements;
+    // the other orders separate rounds by grid barriers
+    if (P.o_v == 0) __threadfence();
+    __syncwarp();
+    if (go && rawvalid) {
+        atomicSub(P.live + vb + rawnbr, 1);
+        if (P.o_v == 0 && ldcg_u8(P.state + vb + rawnbr) == 1) {
+            int old = atomicSub(P.blk + vb + rawnbr, 1);
+            if (old == 1) {
+                int pos = rc.wl_base + atomicAdd(P.ctr + rc.wslot, 1);
+                P.wl[pos] = (unsigned int)(vb + (size_t)rawnbr);
+            }
+        }
+    }
+    if (go && tl == 0) {
+        ls.fills += (unsigned long long)(ovf ? 0 : nf);
+        ls.maxstar = max(ls.maxstar, L);
+        ls.raw += (unsigned long long)lraw;
+        P.state[vb + v] = 2;
+    }
+    __syncwarp();
+    return active && fail;
+}
+
 // ---------------------------------------------------------------------------------------------
 // the persistent elimination kernel
 // ---------------------------------------------------------------------------------------------
 
-// process work-list items [start, end): one warp per item; big stars are deferred to the block phase
+// Run one tier: the items whose bit is set in `mask` (lane i holds item i of the warp's chunk) are handed
+// to the 32 / W tiles of the warp, 32 / W at a time. Returns the mask of items that did not fit.
+template <int W>
+__device__ unsigned run_tier(const SchurParams& P, const RoundCtx& rc, unsigned mask, unsigned int my_idx, LocalStats& ls) {
+    constexpr int TPW = 32 / W;
+    const int lane = threadIdx.x & 31;
+    const int tile = lane / W;
+    unsigned failed = 0;
+    while (mask) {
+        // tile t takes the t-th pending item
+        unsigned src = __fns(mask, 0, tile + 1);            // lane holding that item, 0xffffffff if none
+        unsigned int idx = __shfl_sync(RLAP_FULL_MASK, my_idx, src & 31);
+        if (src == 0xffffffffu) idx = 0xffffffffu;
+        bool f = eliminate_star_tile<W>(P, rc, idx, ls);
+        unsigned fm = __ballot_sync(RLAP_FULL_MASK, f && (lane & (W - 1)) == 0);
+        // translate failing tiles back to item bits and drop the processed items from the mask
+#pragma unroll
+        for (int t = 0; t < TPW; t++) {
+            unsigned s = __fns(mask, 0, 1);
+            if (s == 0xffffffffu) break;
+            if ((fm >> (t * W)) & 1u) failed |= 1u << s;
+            mask &= mask - 1;
+        }
+    }
+    return failed;
+}
+
+// process work-list items [start, end): a warp takes a chunk of up to 32 items and serves them tier by
+// tier (8-, 16-, 32-lane register tiles, then the shared-memory path); big stars go to the block phase
 __device__ void run_warp_items(const SchurParams& P, const RoundCtx& rc, uint64_t* smem, CtaScratch* cs, int start,
                                int end, LocalStats& ls) {
     const int gw = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int nw = (int)((gridDim.x * blockDim.x) >> 5);
     const int lane = threadIdx.x & 31;
     StarBuf sb = warp_buf(smem);
-    for (int it = start + gw; it < end; it += nw) {
-        unsigned int idx = __ldcg(P.wl + it);
-        int view = (int)(idx / (unsigned)P.n), v = (int)(idx % (unsigned)P.n);
-        if (P.o_v != 0) {  // truncated final round of a graph: only the highest ids go
-            size_t seg = (size_t)view * P.G + graph_of(P, v);
-            if (ldcg_i32(P.ovfseg + seg) && idx < __ldcg(P.thresh + seg)) continue;
+    const int count = end - start;
+    if (count <= 0) return;
+    int chunk = (count + nw - 1) / nw;       // spread small rounds over all warps
+    if (chunk > 32) chunk = 32;
+    for (int c0 = start + gw * chunk; c0 < end; c0 += nw * chunk) {
+        const int it = c0 + lane;
+        unsigned int idx = 0xffffffffu;
+        int lv = -1, cls = -1;
+        if (lane < chunk && it < end) {
+            idx = __ldcg(P.wl + it);
+            bool skip = false;
+            if (P.o_v != 0) {  // truncated final round of a graph: only the highest ids go
+                int view = (int)(idx / (unsigned)P.n), v = (int)(idx % (unsigned)P.n);
+                size_t seg = (size_t)view * P.G + graph_of(P, v);
+                skip = ldcg_i32(P.ovfseg + seg) && idx < __ldcg(P.thresh + seg);
+            }
+            if (!skip) {
+                lv = ldcg_i32(P.live + idx);
+                // the register tiles hold the whole raw list: the base segment bounds it from below
+                int v = (int)(idx % (unsigned)P.n);
+                int nb = __ldg(P.ptr + v + 1) - __ldg(P.ptr + v);
+                if (lv <= CAP_WARP) cls = max(lv, nb);
+                else cls = lv;
+            }
         }
-        int lv = ldcg_i32(P.live + idx);
-        if (lv <= CAP_WARP) {
-            eliminate_star<false>(P, rc, view, v, sb, cs, ls);
-        } else if (lane == 0) {
+        if (lv > CAP_WARP) {
             int pos = rc.dl_base + atomicAdd(P.ctr + rc.dslot, 1);
             P.dl[pos] = idx;
+        }
+        unsigned m8 = __ballot_sync(RLAP_FULL_MASK, cls >= 0 && cls <= 8);
+        unsigned m16 = __ballot_sync(RLAP_FULL_MASK, cls > 8 && cls <= 16);
+        unsigned m32 = __ballot_sync(RLAP_FULL_MASK, cls > 16 && cls <= 32);
+        unsigned msm = __ballot_sync(RLAP_FULL_MASK, cls > 32 && lv <= CAP_WARP);
+        m16 |= run_tier<8>(P, rc, m8, idx, ls);
+        m32 |= run_tier<16>(P, rc, m16, idx, ls);
+        msm |= run_tier<32>(P, rc, m32, idx, ls);
+        while (msm) {
+            int k = __ffs(msm) - 1;
+            msm &= msm - 1;
+            unsigned int kidx = __shfl_sync(RLAP_FULL_MASK, idx, k);
+            eliminate_star<false>(P, rc, (int)(kidx / (unsigned)P.n), (int)(kidx % (unsigned)P.n), sb, cs, ls);
         }
     }
 }

@@ -161,4 +161,153 @@ __device__ __forceinline__ unsigned warp_merge_sorted(uint64_t& a, unsigned long
     return hmask;
 }
 
+
+// ascending bitonic sort of (k, a) pairs, one per lane, with payload q
+__device__ __forceinline__ void warp_sort_kaq(uint64_t& k, uint64_t& a, unsigned long long& q) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            uint64_t ok = __shfl_xor_sync(RLAP_FULL_MASK, k, j);
+            uint64_t oa = __shfl_xor_sync(RLAP_FULL_MASK, a, j);
+            unsigned long long oq = __shfl_xor_sync(RLAP_FULL_MASK, q, j);
+            bool take_min = (((lane & j) == 0) == ((lane & kk) == 0));
+            bool lt = (k < ok) || (k == ok && a < oa);
+            bool keep = (take_min == lt);
+            k = keep ? k : ok;
+            a = keep ? a : oa;
+            q = keep ? q : oq;
+        }
+    }
+}
+
+// first lane index in [0, L) whose C exceeds r (L if none); every lane may ask for a different r
+__device__ __forceinline__ int warp_upper_bound(unsigned long long C, int L, unsigned long long r) {
+    int lo = 0, hi = L;
+#pragma unroll
+    for (int it = 0; it < 6; it++) {
+        int mid = (lo + hi) >> 1;
+        unsigned long long cm = __shfl_sync(RLAP_FULL_MASK, C, mid & 31);
+        if (lo < hi) {
+            if (cm > r) hi = mid; else lo = mid + 1;
+        }
+    }
+    return lo;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// sub-warp tiles: W lanes (8, 16 or 32) hold one star; 32 / W stars per warp run in lock step
+// ---------------------------------------------------------------------------------------------
+template <int W> struct Tile {
+    static __device__ __forceinline__ int tl() { return (int)(threadIdx.x & (W - 1)); }
+    static __device__ __forceinline__ int tbase() { return (int)(threadIdx.x & 31 & ~(W - 1)); }
+    static __device__ __forceinline__ unsigned low() { return W == 32 ? 0xffffffffu : ((1u << W) - 1u); }
+    static __device__ __forceinline__ unsigned ballot(bool pred) {
+        return (__ballot_sync(RLAP_FULL_MASK, pred) >> tbase()) & low();
+    }
+    static __device__ __forceinline__ uint64_t sort_u64(uint64_t a) {
+        const int l = tl();
+#pragma unroll
+        for (int k = 2; k <= W; k <<= 1) {
+#pragma unroll
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                uint64_t o = __shfl_xor_sync(RLAP_FULL_MASK, a, j, W);
+                bool take_min = (((l & j) == 0) == ((l & k) == 0));
+                bool lt = a < o;
+                a = (take_min == lt) ? a : o;
+            }
+        }
+        return a;
+    }
+    static __device__ __forceinline__ void sort_kaq(uint64_t& k, uint64_t& a, unsigned long long& q) {
+        const int l = tl();
+#pragma unroll
+        for (int kk = 2; kk <= W; kk <<= 1) {
+#pragma unroll
+            for (int j = kk >> 1; j > 0; j >>= 1) {
+                uint64_t ok = __shfl_xor_sync(RLAP_FULL_MASK, k, j, W);
+                uint64_t oa = __shfl_xor_sync(RLAP_FULL_MASK, a, j, W);
+                unsigned long long oq = __shfl_xor_sync(RLAP_FULL_MASK, q, j, W);
+                bool take_min = (((l & j) == 0) == ((l & kk) == 0));
+                bool lt = (k < ok) || (k == ok && a < oa);
+                bool keep = (take_min == lt);
+                k = keep ? k : ok;
+                a = keep ? a : oa;
+                q = keep ? q : oq;
+            }
+        }
+    }
+    static __device__ __forceinline__ uint32_t max_u32(uint32_t v) {
+#pragma unroll
+        for (int d = W / 2; d > 0; d >>= 1) v = max(v, __shfl_xor_sync(RLAP_FULL_MASK, v, d, W));
+        return v;
+    }
+    static __device__ __forceinline__ unsigned long long incl_scan(unsigned long long v) {
+        const int l = tl();
+#pragma unroll
+        for (int d = 1; d < W; d <<= 1) {
+            unsigned long long t = __shfl_up_sync(RLAP_FULL_MASK, v, d, W);
+            if (l >= d) v += t;
+        }
+        return v;
+    }
+    // first tile-lane index in [0, L) whose C exceeds r (L if none)
+    static __device__ __forceinline__ int upper_bound(unsigned long long C, int L, unsigned long long r) {
+        int lo = 0, hi = L;
+        constexpr int ITERS = (W == 32 ? 6 : W == 16 ? 5 : 4);
+#pragma unroll
+        for (int it = 0; it < ITERS; it++) {
+            int mid = (lo + hi) >> 1;
+            unsigned long long cm = __shfl_sync(RLAP_FULL_MASK, C, mid & (W - 1), W);
+            if (lo < hi) {
+                if (cm > r) hi = mid; else lo = mid + 1;
+            }
+        }
+        return lo;
+    }
+    // merge runs of equal neighbour of a sorted tile star; see warp_merge_sorted
+    static __device__ __forceinline__ unsigned merge_sorted(uint64_t& a, unsigned long long& q, int& shift, bool need_q) {
+        const int l = tl();
+        const bool valid = a != RLAP_PAD_A;
+        const uint32_t nb = a_nbr(a);
+        const uint32_t pnb = __shfl_up_sync(RLAP_FULL_MASK, nb, 1, W);
+        const bool head = valid && (l == 0 || pnb != nb);
+        const unsigned vmask = ballot(valid);
+        const unsigned hmask = ballot(head);
+        q = 0;
+        shift = 0;
+        const bool dups = hmask != vmask;
+        const bool anyd = __any_sync(RLAP_FULL_MASK, dups);   // keep the tiles of a warp in lock step
+        uint32_t wmaxb = max_u32(valid ? (uint32_t)a : 0u);
+        if (vmask != 0 && (dups || need_q)) {
+            shift = star_shift(__uint_as_float(wmaxb), __popc(vmask));
+            q = valid ? quantize(a_w(a), shift) : 0ull;
+        }
+        if (anyd) {
+            unsigned long long qs = q;
+            int cnt = valid ? 1 : 0;
+#pragma unroll
+            for (int d = 1; d < W; d <<= 1) {
+                unsigned long long oq = __shfl_down_sync(RLAP_FULL_MASK, qs, d, W);
+                int oc = __shfl_down_sync(RLAP_FULL_MASK, cnt, d, W);
+                uint32_t onb = __shfl_down_sync(RLAP_FULL_MASK, nb, d, W);
+                bool ov = (l + d < W) && ((vmask >> ((l + d) & (W - 1))) & 1u);
+                if (dups && valid && ov && onb == nb) { qs += oq; cnt += oc; }
+            }
+            if (dups) {
+                if (head) {
+                    q = qs;
+                    if (cnt > 1) a = ((uint64_t)nb << 32) | (uint64_t)__float_as_uint(dequantize(qs, shift));
+                } else if (valid) {
+                    q = 0;
+                    a = ((uint64_t)nb << 32) | (uint64_t)RLAP_DEAD_W;
+                }
+            }
+        }
+        return hmask;
+    }
+};
+
 }  // namespace rlap
