@@ -90,7 +90,9 @@ int rlap_schur_eliminate(int64_t n, int64_t nnz, const int32_t* csr_ptr, const i
                          int64_t* stats /* HOST int64[16] or NULL, see below */, void* stream);
 /* stats: [0] rounds, [1] fill edges, [2] max pool entries used by a view, [3] largest merged star,
  * [4] raw adjacency entries read at elimination, [5] output rows, [6] pool_cap used,
- * [7] elimination kernel time (us, CUDA events), [8] emission count pass time (us). */
+ * [7] elimination kernel time (us, CUDA events), [8] emission count pass time (us),
+ * [9..14] time inside the elimination kernel (us): init, min-key scan, candidate selection, truncation,
+ * warp-level elimination, block-level elimination. */
 
 /* ---- emission (replaces the output assembly, preconditioner.cc:435-457 / 789-810 / 916-934) ------
  * Writes the rows of all views back to back, view after view, each view sorted by (col, row):

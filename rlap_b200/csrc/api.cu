@@ -337,6 +337,7 @@ int rlap_schur_eliminate(int64_t n, int64_t nnz, const int32_t* csr_ptr, const i
         cudaEventElapsedTime(&ms_count, ev[1], ev[2]);
         stats[7] = (int64_t)(ms_elim * 1000.0f);   // k_eliminate, microseconds
         stats[8] = (int64_t)(ms_count * 1000.0f);  // emission count pass + scan, microseconds
+        for (int i = 0; i < 6; i++) stats[9 + i] = (int64_t)(hstats[ST_T_INIT + i] / 1000);  // phase times, us
     }
     {
         std::lock_guard<std::mutex> lk(g_layout_mutex);

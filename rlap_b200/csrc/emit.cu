@@ -78,16 +78,25 @@ __device__ void emit_sort_staged(const SchurParams& P, size_t idx, StarBuf sb, C
         return;
     }
     uint32_t wmaxb = 0;
-    for (int i = r; i < lraw; i += gs) {
-        uint64_t a = P.raw[off + i];
+    const int P2 = next_pow2(lraw);
+    for (int i = r; i < P2; i += gs) {
+        uint64_t a = (i < lraw) ? P.raw[off + i] : RLAP_PAD_A;
         sb.A[i] = a;
-        wmaxb = max(wmaxb, (uint32_t)a);
+        if (i < lraw) wmaxb = max(wmaxb, (uint32_t)a);
     }
-    wmaxb = g_max_u32<CTA>(wmaxb, cs);
     g_sync<CTA>();
-    int P2 = 0;
-    const int shift = star_shift(__uint_as_float(wmaxb), lraw);
-    const int L = star_sort_merge<CTA>(sb, lraw, shift, cs, &P2);
+    g_bitonic_sort_keys<CTA>(sb.A, P2);
+    // multi-edges are rare among survivors: look for one before paying for the fixed-point merge
+    int dup = 0;
+    for (int i = r + 1; i < lraw; i += gs) dup |= (a_nbr(sb.A[i]) == a_nbr(sb.A[i - 1]));
+    dup = CTA ? __syncthreads_or(dup) : __any_sync(RLAP_FULL_MASK, dup);
+    int L = lraw;
+    if (dup) {
+        wmaxb = g_max_u32<CTA>(wmaxb, cs);
+        g_sync<CTA>();
+        const int shift = star_shift(__uint_as_float(wmaxb), lraw);
+        L = star_merge_sorted<CTA>(sb, lraw, shift, cs);
+    }
     int carry = 0;
     for (int base = 0; base < lraw; base += gs) {
         int i = base + r;

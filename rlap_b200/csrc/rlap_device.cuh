@@ -222,6 +222,24 @@ __device__ __forceinline__ void g_bitonic_sort(StarBuf sb, int P) {
     }
 }
 
+// key-only variant: sorts A ascending, nothing else moves
+template <bool CTA>
+__device__ __forceinline__ void g_bitonic_sort_keys(uint64_t* A, int P) {
+    const int gs = g_size<CTA>(), r = g_rank<CTA>();
+    for (int k = 2; k <= P; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = r; t < (P >> 1); t += gs) {
+                int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                int l = i | j;
+                bool up = ((i & k) == 0);
+                uint64_t a1 = A[i], a2 = A[l];
+                if (up ? (a2 < a1) : (a1 < a2)) { A[i] = a2; A[l] = a1; }
+            }
+            g_sync<CTA>();
+        }
+    }
+}
+
 __device__ __forceinline__ int next_pow2(int x) { return x <= 1 ? 1 : 1 << (32 - __clz(x - 1)); }
 
 // first index in C[0..len) with C[idx] > r  (len if none)

@@ -123,6 +123,7 @@ __device__ int star_gather(const SchurParams& P, int view, int v, StarBuf sb, Ct
     return cnt;
 }
 
+template <bool LIVE>
 __device__ __forceinline__ void push_entry(const SchurParams& P, size_t vb, int4* pool, int owner, int nbr, float w,
                                            int slot) {
     int4 en;
@@ -131,25 +132,35 @@ __device__ __forceinline__ void push_entry(const SchurParams& P, size_t vb, int4
     en.z = atomicExch(P.head + vb + owner, slot);
     en.w = owner;
     pool[slot] = en;
-    atomicAdd(P.live + vb + owner, 1);
+    if (LIVE) atomicAdd(P.live + vb + owner, 1);
 }
 
-// fill edge (j,k,w): append to both endpoints; o_v = random also records the new dependency
-__device__ __forceinline__ void push_fill(const SchurParams& P, size_t vb, int4* pool, int j, int k, float w,
+// fill edge (j,k,w): append to both endpoints; o_v = random also records the new dependency.
+// LIVE: bump the live counters of both endpoints here (the register tiles apply net deltas instead).
+// Returns false for an underflowed fill (weight 0: not created).
+template <bool LIVE>
+__device__ __forceinline__ bool push_fill(const SchurParams& P, size_t vb, int4* pool, int j, int k, float w,
                                           long long slot) {
     if (!(w > 0.f)) {  // underflowed fill: leave two tombstones so that the pool can be read linearly
         pool[slot] = make_int4(-1, 0, -1, -1);
         pool[slot + 1] = make_int4(-1, 0, -1, -1);
-        return;
+        return false;
     }
-    push_entry(P, vb, pool, j, k, w, (int)slot);
-    push_entry(P, vb, pool, k, j, w, (int)slot + 1);
+    {   // both list heads are exchanged before either entry is written: the two round trips overlap
+        const int s0 = (int)slot, s1 = (int)slot + 1;
+        const int n0 = atomicExch(P.head + vb + j, s0);
+        const int n1 = atomicExch(P.head + vb + k, s1);
+        pool[s0] = make_int4(k, __float_as_int(w), n0, j);
+        pool[s1] = make_int4(j, __float_as_int(w), n1, k);
+        if (LIVE) { atomicAdd(P.live + vb + j, 1); atomicAdd(P.live + vb + k, 1); }
+    }
     if (P.o_v == 0) {
         if (ldcg_u8(P.state + vb + j) == 1 && ldcg_u8(P.state + vb + k) == 1) {
             int rj = ldcg_i32(P.rank + vb + j), rk = ldcg_i32(P.rank + vb + k);
             if (rj < rk) atomicAdd(P.blk + vb + k, 1); else atomicAdd(P.blk + vb + j, 1);
         }
     }
+    return true;
 }
 
 // Eliminate vertex v of `view` (A.2 clique sampling / A.4 coarsening / full clique), DESIGN.md §3.3.
@@ -218,7 +229,7 @@ __device__ void eliminate_star(const SchurParams& P, const RoundCtx& rc, int vie
                     for (int b2 = a + 1 + r; b2 < L; b2 += gs) {
                         const uint64_t eb = sb.A[b2];
                         float w = __double2float_rn(__ddiv_rn(__dmul_rn((double)a_w(ea), (double)a_w(eb)), Sf));
-                        push_fill(P, vb, pool, (int)a_nbr(ea), (int)a_nbr(eb), w, slot0 + 2 * (off + (b2 - a - 1)));
+                        push_fill<true>(P, vb, pool, (int)a_nbr(ea), (int)a_nbr(eb), w, slot0 + 2 * (off + (b2 - a - 1)));
                     }
                 }
             } else if (coarsen) {
@@ -235,7 +246,7 @@ __device__ void eliminate_star(const SchurParams& P, const RoundCtx& rc, int vie
                     const double wm = (double)a_w(em);
                     float w = __double2float_rn(__ddiv_rn(__dmul_rn(wk, wm), __dadd_rn(wk, wm)));
                     int sl = m < koff ? m : m - 1;
-                    push_fill(P, vb, pool, (int)a_nbr(em), (int)a_nbr(ek), w, slot0 + 2LL * sl);
+                    push_fill<true>(P, vb, pool, (int)a_nbr(em), (int)a_nbr(ek), w, slot0 + 2LL * sl);
                 }
             } else {
                 for (int m = r; m < L - 1; m += gs) {
@@ -249,7 +260,7 @@ __device__ void eliminate_star(const SchurParams& P, const RoundCtx& rc, int vie
                     if (koff >= L) koff = L - 1;
                     float w = __double2float_rn(
                         __ddiv_rn(__dmul_rn((double)a_w(em), __ull2double_rn(rem)), __ull2double_rn(S)));
-                    push_fill(P, vb, pool, (int)a_nbr(em), (int)a_nbr(sb.A[koff]), w, slot0 + 2LL * m);
+                    push_fill<true>(P, vb, pool, (int)a_nbr(em), (int)a_nbr(sb.A[koff]), w, slot0 + 2LL * m);
                 }
             }
         }
@@ -286,8 +297,10 @@ __device__ void eliminate_star(const SchurParams& P, const RoundCtx& rc, int vie
 // item (uniform inside the tile) or 0xffffffff for an idle tile. Returns true for the lanes of a tile
 // whose star did not fit (raw list, dead entries included, longer than W): nothing was done for it and
 // the caller retries on a wider tile or the shared-memory path. Same arithmetic, same result.
+// `slot0` / `nslots`: pool slots reserved for this star by the caller (an upper bound, 2 per possible fill).
 template <int W>
-__device__ bool eliminate_star_tile(const SchurParams& P, const RoundCtx& rc, unsigned int idx, LocalStats& ls) {
+__device__ bool eliminate_star_tile(const SchurParams& P, const RoundCtx& rc, unsigned int idx, long long slot0,
+                                    int nslots, LocalStats& ls) {
     typedef Tile<W> T;
     const int tl = T::tl();
     const bool active = idx != 0xffffffffu;
@@ -324,8 +337,12 @@ __device__ bool eliminate_star_tile(const SchurParams& P, const RoundCtx& rc, un
     const int lraw = __popc(T::ballot(rawvalid));
     unsigned long long q;
     int shift;
-    const unsigned hmask = T::merge_sorted(a, q, shift, true);
+    int mult;
+    const unsigned hmask = T::merge_sorted(a, q, shift, true, mult);
     const int L = __popc(hmask);
+    // live counters: a neighbour loses its entries to v (all `mult` of them) and gains one entry per fill it
+    // receives. The extra multiplicity goes now, the rest is netted per merged neighbour after sampling.
+    if (go && ((hmask >> tl) & 1u) && mult > 1) atomicSub(P.live + vb + rawnbr, mult - 1);
     const bool live = (hmask >> tl) & 1u;
     const bool full = (P.flags & 1) != 0;
     const bool coarsen = (P.o_v == 2) && !full;
@@ -346,24 +363,26 @@ __device__ bool eliminate_star_tile(const SchurParams& P, const RoundCtx& rc, un
     const unsigned long long C = T::incl_scan(q);
     const unsigned long long S = __shfl_sync(RLAP_FULL_MASK, C, (L > 0 ? L - 1 : 0), W);
     const long long nf = (L < 1) ? 0 : (full ? (long long)L * (L - 1) / 2 : (long long)(L - 1));
-    long long slot0 = 0;
-    {
-        unsigned long long s0 = 0;
-        if (go && tl == 0 && nf > 0) s0 = atomicAdd(P.pool_cursor + view, (unsigned long long)(2 * nf));
-        slot0 = (long long)__shfl_sync(RLAP_FULL_MASK, s0, 0, W);
-    }
-    const bool ovf = nf > 0 && slot0 + 2 * nf > P.pool_cap;
+    const bool ovf = nslots > 0 && slot0 + nslots > P.pool_cap;
     if (go && ovf && tl == 0) set_status(P, 5);
     const bool emit = go && nf > 0 && !ovf;
+    // reserved but unused slots (multi-edges merged): tombstones, the pool is read linearly at emission
+    if (go && !ovf)
+        for (long long u = 2 * nf + tl; u < nslots; u += W) pool[slot0 + u] = make_int4(-1, 0, -1, -1);
+    int delta = -1;   // net change of live[neighbour] for the merged neighbour held by this lane
     if (full) {
         const double Sf = __dmul_rn(__ull2double_rn(S), pow2d(-shift));
         for (int b2 = 1; b2 < W; b2++) {
             const uint64_t eb = __shfl_sync(RLAP_FULL_MASK, a, b2, W);
+            bool done = false;
             if (emit && b2 < L && tl < b2) {
                 float w = __double2float_rn(__ddiv_rn(__dmul_rn((double)a_w(a), (double)a_w(eb)), Sf));
                 long long off = (long long)tl * (2LL * L - tl - 1) / 2;
-                push_fill(P, vb, pool, (int)a_nbr(a), (int)a_nbr(eb), w, slot0 + 2 * (off + (b2 - tl - 1)));
+                done = push_fill<false>(P, vb, pool, (int)a_nbr(a), (int)a_nbr(eb), w, slot0 + 2 * (off + (b2 - tl - 1)));
             }
+            unsigned dm = T::ballot(done);
+            if (done) delta++;
+            if (tl == b2) delta += __popc(dm);
         }
     } else if (coarsen) {
         uint4 x = philox4x32_10(P.k0, P.k1, (uint32_t)v, 0xffffffffu, view_id, TAG_PICK);
@@ -372,12 +391,16 @@ __device__ bool eliminate_star_tile(const SchurParams& P, const RoundCtx& rc, un
         if (koff >= L) koff = L - 1;
         if (koff < 0) koff = 0;
         const uint64_t ek = __shfl_sync(RLAP_FULL_MASK, a, koff, W);
+        bool done = false;
         if (emit && tl < L && tl != koff) {
             const double wk = (double)a_w(ek), wm = (double)a_w(a);
             float w = __double2float_rn(__ddiv_rn(__dmul_rn(wk, wm), __dadd_rn(wk, wm)));
             int sl = tl < koff ? tl : tl - 1;
-            push_fill(P, vb, pool, (int)a_nbr(a), (int)a_nbr(ek), w, slot0 + 2LL * sl);
+            done = push_fill<false>(P, vb, pool, (int)a_nbr(a), (int)a_nbr(ek), w, slot0 + 2LL * sl);
         }
+        unsigned dm = T::ballot(done);
+        if (done) delta++;
+        if (tl == koff) delta += __popc(dm);
     } else {
         const bool act = tl < L - 1;
         unsigned long long rr = 0, rem = 0;
@@ -393,15 +416,18 @@ __device__ bool eliminate_star_tile(const SchurParams& P, const RoundCtx& rc, un
         const uint64_t ek = __shfl_sync(RLAP_FULL_MASK, a, koff, W);
         if (emit && act) {
             float w = __double2float_rn(__ddiv_rn(__dmul_rn((double)a_w(a), __ull2double_rn(rem)), __ull2double_rn(S)));
-            push_fill(P, vb, pool, (int)a_nbr(a), (int)a_nbr(ek), w, slot0 + 2LL * tl);
+            if (push_fill<false>(P, vb, pool, (int)a_nbr(a), (int)a_nbr(ek), w, slot0 + 2LL * tl)) {
+                delta++;
+                atomicAdd(P.live + vb + (int)a_nbr(ek), 1);
+            }
         }
     }
     // o_v = random: pushes and dependency increments are ordered before the decrements;
     // the other orders separate rounds by grid barriers
     if (P.o_v == 0) __threadfence();
     __syncwarp();
+    if (go && tl < L && delta != 0) atomicAdd(P.live + vb + (int)a_nbr(a), delta);
     if (go && rawvalid) {
-        atomicSub(P.live + vb + rawnbr, 1);
         if (P.o_v == 0 && ldcg_u8(P.state + vb + rawnbr) == 1) {
             int old = atomicSub(P.blk + vb + rawnbr, 1);
             if (old == 1) {
@@ -427,7 +453,8 @@ __device__ bool eliminate_star_tile(const SchurParams& P, const RoundCtx& rc, un
 // Run one tier: the items whose bit is set in `mask` (lane i holds item i of the warp's chunk) are handed
 // to the 32 / W tiles of the warp, 32 / W at a time. Returns the mask of items that did not fit.
 template <int W>
-__device__ unsigned run_tier(const SchurParams& P, const RoundCtx& rc, unsigned mask, unsigned int my_idx, LocalStats& ls) {
+__device__ unsigned run_tier(const SchurParams& P, const RoundCtx& rc, unsigned mask, unsigned int my_idx,
+                             long long my_slot0, int my_nslots, LocalStats& ls) {
     constexpr int TPW = 32 / W;
     const int lane = threadIdx.x & 31;
     const int tile = lane / W;
@@ -436,8 +463,10 @@ __device__ unsigned run_tier(const SchurParams& P, const RoundCtx& rc, unsigned 
         // tile t takes the t-th pending item
         unsigned src = __fns(mask, 0, tile + 1);            // lane holding that item, 0xffffffff if none
         unsigned int idx = __shfl_sync(RLAP_FULL_MASK, my_idx, src & 31);
+        long long sl0 = __shfl_sync(RLAP_FULL_MASK, my_slot0, src & 31);
+        int nsl = __shfl_sync(RLAP_FULL_MASK, my_nslots, src & 31);
         if (src == 0xffffffffu) idx = 0xffffffffu;
-        bool f = eliminate_star_tile<W>(P, rc, idx, ls);
+        bool f = eliminate_star_tile<W>(P, rc, idx, sl0, nsl, ls);
         unsigned fm = __ballot_sync(RLAP_FULL_MASK, f && (lane & (W - 1)) == 0);
         // translate failing tiles back to item bits and drop the processed items from the mask
 #pragma unroll
@@ -492,9 +521,47 @@ __device__ void run_warp_items(const SchurParams& P, const RoundCtx& rc, uint64_
         unsigned m16 = __ballot_sync(RLAP_FULL_MASK, cls > 8 && cls <= 16);
         unsigned m32 = __ballot_sync(RLAP_FULL_MASK, cls > 16 && cls <= 32);
         unsigned msm = __ballot_sync(RLAP_FULL_MASK, cls > 32 && lv <= CAP_WARP);
-        m16 |= run_tier<8>(P, rc, m8, idx, ls);
-        m32 |= run_tier<16>(P, rc, m16, idx, ls);
-        msm |= run_tier<32>(P, rc, m32, idx, ls);
+        // pool slots for the register tiers are reserved once per chunk: 2 per possible fill (L <= live), one
+        // atomic per view present in the chunk instead of one per star
+        const bool full = (P.flags & 1) != 0;
+        int nslots = 0;
+        if (lv >= 2 && cls <= 32) nslots = full ? lv * (lv - 1) : 2 * (lv - 1);
+        long long slot0 = 0;
+        {
+            const int view = (idx == 0xffffffffu) ? -1 : (int)(idx / (unsigned)P.n);
+            int incl = nslots;  // inclusive prefix over the lanes of the chunk
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                int t = __shfl_up_sync(RLAP_FULL_MASK, incl, d);
+                if (lane >= d) incl += t;
+            }
+            const unsigned need = __ballot_sync(RLAP_FULL_MASK, nslots > 0);
+            if (need) {
+                const int first = __ffs(need) - 1, last = 31 - __clz(need);
+                const int v0 = __shfl_sync(RLAP_FULL_MASK, view, first);
+                const bool same = __all_sync(RLAP_FULL_MASK, nslots == 0 || view == v0);
+                if (same) {
+                    const int total = __shfl_sync(RLAP_FULL_MASK, incl, last);
+                    unsigned long long b0 = 0;
+                    if (lane == first) b0 = atomicAdd(P.pool_cursor + v0, (unsigned long long)total);
+                    b0 = __shfl_sync(RLAP_FULL_MASK, b0, first);
+                    slot0 = (long long)b0 + incl - nslots;
+                } else if (nslots > 0) {
+                    slot0 = (long long)atomicAdd(P.pool_cursor + view, (unsigned long long)nslots);
+                }
+            }
+        }
+        m16 |= run_tier<8>(P, rc, m8, idx, slot0, nslots, ls);
+        m32 |= run_tier<16>(P, rc, m16, idx, slot0, nslots, ls);
+        msm |= run_tier<32>(P, rc, m32, idx, slot0, nslots, ls);
+        // stars that fell through every register tier keep their reservation unused: tombstone it
+        {
+            unsigned fell = msm & __ballot_sync(RLAP_FULL_MASK, nslots > 0);
+            if (((fell >> lane) & 1u) && slot0 + nslots <= P.pool_cap) {
+                int4* pool = P.pool + (size_t)(idx / (unsigned)P.n) * (size_t)P.pool_cap;
+                for (int u = 0; u < nslots; u++) pool[slot0 + u] = make_int4(-1, 0, -1, -1);
+            }
+        }
         while (msm) {
             int k = __ffs(msm) - 1;
             msm &= msm - 1;
@@ -569,6 +636,17 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
     for (long long s = tid; s < P.V; s += nthr) P.pool_cursor[s] = 0ull;
     grid.sync();
 
+    // phase timing (block 0, thread 0; nanoseconds between grid barriers, waits included)
+    unsigned long long tmark = 0;
+    auto lap = [&](int slot) {
+        if (tid == 0) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (slot >= 0) P.stats[slot] += now - tmark;
+            tmark = now;
+        }
+    };
+    lap(-1);
     int wl_start = 0;   // first unconsumed work-list item
     int dl_start = 0;
     int rounds = 0;
@@ -625,6 +703,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
             }
         }
         grid.sync();
+        lap(ST_T_INIT);
         while (true) {
             // items to consume were appended in the previous round
             int wl_end = wl_start + ldcg_i32(P.ctr + CTR_WCNT0 + (rounds + 2) % 3);
@@ -635,15 +714,18 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
             run_warp_items(P, rc, smem, &cs, wl_start, wl_end, ls);
             wl_start = wl_end;
             grid.sync();
+            lap(ST_T_D1);
             int dl_end = dl_start + ldcg_i32(P.ctr + rc.dslot);
             if (dl_end != dl_start) {
                 run_block_items(P, rc, smem, &cs, dl_start, dl_end, ls);
                 dl_start = dl_end;
                 grid.sync();
+                lap(ST_T_D2);
             }
             rounds++;
         }
     } else {
+        lap(ST_T_INIT);
         // degree / coarsen: rounds over the minimum-key bucket of every (view, graph) segment
         while (true) {
             const int par = rounds & 1;
@@ -658,36 +740,51 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
             }
             for (long long s = tid; s < VG; s += nthr) { mk_other[s] = 0x7fffffff; P.cntI[s] = 0; P.ovfseg[s] = 0; }
             {
-                int* smin = (int*)smem;  // the star buffers are idle during this phase
-                const bool use_smem = VG <= (long long)(3 * CAP_CTA * 2);
+                // the star buffers are idle during this phase: per-segment minima are reduced in shared memory and
+                // the per-segment `rem` values are read from a shared copy (every warp of the grid asking L2 for
+                // the same one or two lines is a hot spot)
+                int* smin = (int*)smem;
+                int* srem = smin + VG;
+                const bool use_smem = VG <= (long long)(3 * CAP_CTA);
                 if (use_smem) {
-                    for (int q = threadIdx.x; q < (int)VG; q += blockDim.x) smin[q] = 0x7fffffff;
+                    for (int q = threadIdx.x; q < (int)VG; q += blockDim.x) { smin[q] = 0x7fffffff; srem[q] = ldcg_i32(P.rem + q); }
                     __syncthreads();
                 }
                 bool any = false;
-                for (unsigned base = (unsigned)(tid - lane); base < uVN; base += (unsigned)nthr) {
-                    unsigned idx = base + lane;
-                    bool valid = false;
-                    int key = 0x7fffffff, seg = 0;
-                    if (idx < uVN) {
-                        uint8_t st = ldcg_u8(P.state + idx);
-                        if (st != 2) {
+                // four independent elements per thread and iteration; every load is issued before the first use,
+                // so one memory round trip serves four vertices
+                for (unsigned base = (unsigned)(tid - lane); base < uVN; base += 4u * (unsigned)nthr) {
+                    uint8_t st4[4];
+                    int lv4[4], rm4[4], sg4[4];
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; q4++) {
+                        const unsigned idx = base + (unsigned)q4 * (unsigned)nthr + lane;
+                        st4[q4] = 2; lv4[q4] = 0; rm4[q4] = 0; sg4[q4] = 0;
+                        if (idx < uVN) {
                             int view = (int)(idx / un), v = (int)(idx % un);
-                            seg = view * P.G + graph_of(P, v);
-                            if (ldcg_i32(P.rem + seg) > 0) { valid = true; key = key_eff(P, idx, st); }
+                            sg4[q4] = view * P.G + graph_of(P, v);
+                            st4[q4] = ldcg_u8(P.state + idx);
+                            lv4[q4] = ldcg_i32(P.live + idx);
+                            rm4[q4] = use_smem ? srem[sg4[q4]] : ldcg_i32(P.rem + sg4[q4]);
                         }
                     }
-                    unsigned vm = __ballot_sync(RLAP_FULL_MASK, valid);
-                    if (vm == 0) continue;
-                    any = true;
-                    int leader = __ffs(vm) - 1;
-                    int seg0 = __shfl_sync(RLAP_FULL_MASK, seg, leader);
-                    bool same = __all_sync(RLAP_FULL_MASK, !valid || seg == seg0);
-                    if (same) {
-                        int k = __reduce_min_sync(RLAP_FULL_MASK, key);
-                        if (lane == leader) { if (use_smem) atomicMin(smin + seg0, k); else atomicMin(mk + seg0, k); }
-                    } else if (valid) {
-                        if (use_smem) atomicMin(smin + seg, key); else atomicMin(mk + seg, key);
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; q4++) {
+                        const bool valid = st4[q4] != 2 && rm4[q4] > 0;
+                        const int seg = sg4[q4];
+                        const int key = valid ? ((st4[q4] == 4) ? 0 : max(lv4[q4], 1)) : 0x7fffffff;
+                        unsigned vm = __ballot_sync(RLAP_FULL_MASK, valid);
+                        if (vm == 0) continue;
+                        any = true;
+                        int leader = __ffs(vm) - 1;
+                        int seg0 = __shfl_sync(RLAP_FULL_MASK, seg, leader);
+                        bool same = __all_sync(RLAP_FULL_MASK, !valid || seg == seg0);
+                        if (same) {
+                            int k = __reduce_min_sync(RLAP_FULL_MASK, key);
+                            if (lane == leader) { if (use_smem) atomicMin(smin + seg0, k); else atomicMin(mk + seg0, k); }
+                        } else if (valid) {
+                            if (use_smem) atomicMin(smin + seg, key); else atomicMin(mk + seg, key);
+                        }
                     }
                 }
                 if (use_smem) {
@@ -701,61 +798,119 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
                 if (any && lane == 0) P.ctr[CTR_ACTIVE0 + par] = 1;
             }
             grid.sync();
+            lap(ST_T_A);
             if (ldcg_i32(P.ctr + CTR_ACTIVE0 + par) == 0) break;
             // phase B: members of the minimum bucket with no bucket neighbour of higher id
-            for (unsigned base = (unsigned)(tid - lane); base < uVN; base += (unsigned)nthr) {
-                unsigned idx = base + lane;
-                bool cand = false;
-                int seg = 0, rm = 0;
-                if (idx < uVN) {
-                    uint8_t st = ldcg_u8(P.state + idx);
-                    if (st != 2) {
+            // shared memory during this phase (the star buffers are idle): per-segment rem / min-key copies and
+            // candidate counters (if there are few enough segments), and a candidate buffer per warp so that the
+            // work-list tail is bumped once per ~500 candidates instead of once per warp ballot
+            constexpr int SEG_SM = 1024, WBUF = 512;
+            int* srem = (int*)smem;
+            int* smk = srem + SEG_SM;
+            int* scnt = smk + SEG_SM;
+            unsigned int* wbuf = (unsigned int*)((int*)smem + 4096) + (size_t)(threadIdx.x >> 5) * WBUF;
+            int wfill = 0;
+            const bool bsm = VG <= (long long)SEG_SM;
+            if (bsm) {
+                for (int q = threadIdx.x; q < (int)VG; q += blockDim.x) {
+                    srem[q] = ldcg_i32(P.rem + q); smk[q] = ldcg_i32(mk + q); scnt[q] = 0;
+                }
+                __syncthreads();
+            }
+            auto flush = [&]() {
+                if (wfill == 0) return;
+                int pos0 = 0;
+                if (lane == 0) pos0 = atomicAdd(P.ctr + rc.wslot, wfill);
+                pos0 = __shfl_sync(RLAP_FULL_MASK, pos0, 0);
+                __syncwarp();
+                for (int i = lane; i < wfill; i += 32) P.wl[rc.wl_base + pos0 + i] = wbuf[i];
+                __syncwarp();
+                wfill = 0;
+            };
+            for (unsigned base = (unsigned)(tid - lane); base < uVN; base += 4u * (unsigned)nthr) {
+                uint8_t st4[4];
+                int lv4[4], rm4[4], sg4[4], mk4[4];
+#pragma unroll
+                for (int q4 = 0; q4 < 4; q4++) {
+                    const unsigned idx = base + (unsigned)q4 * (unsigned)nthr + lane;
+                    st4[q4] = 2; lv4[q4] = 0; rm4[q4] = 0; sg4[q4] = 0; mk4[q4] = -1;
+                    if (idx < uVN) {
                         int view = (int)(idx / un), v = (int)(idx % un);
-                        size_t vb = (size_t)view * P.n;
-                        seg = view * P.G + graph_of(P, v);
-                        rm = ldcg_i32(P.rem + seg);
-                        if (rm > 0) {
-                            int m = ldcg_i32(mk + seg);
-                            if (key_eff(P, idx, st) == m) {
-                                bool ok = true;
-                                for (int p = __ldg(P.ptr + v), e = __ldg(P.ptr + v + 1); p < e && ok; p++) {
-                                    int u = __ldg(P.col + p);
-                                    if (u > v && ldcg_u8(P.state + vb + u) != 2 && key_nbr(P, vb, u) == m) ok = false;
-                                }
-                                const int4* pool = P.pool + (size_t)view * (size_t)P.pool_cap;
-                                for (int p = ldcg_i32(P.head + idx); p >= 0 && ok;) {
-                                    int4 en = __ldcg(pool + p);
-                                    if (en.x > v && ldcg_u8(P.state + vb + en.x) != 2 && key_nbr(P, vb, en.x) == m) ok = false;
-                                    p = en.z;
-                                }
-                                cand = ok;
+                        sg4[q4] = view * P.G + graph_of(P, v);
+                        st4[q4] = ldcg_u8(P.state + idx);
+                        lv4[q4] = ldcg_i32(P.live + idx);
+                        rm4[q4] = bsm ? srem[sg4[q4]] : ldcg_i32(P.rem + sg4[q4]);
+                        mk4[q4] = bsm ? smk[sg4[q4]] : ldcg_i32(mk + sg4[q4]);
+                    }
+                }
+#pragma unroll
+                for (int q4 = 0; q4 < 4; q4++) {
+                    const unsigned idx = base + (unsigned)q4 * (unsigned)nthr + lane;
+                    const int seg = sg4[q4], rm = rm4[q4], m = mk4[q4];
+                    bool cand = false;
+                    if (st4[q4] != 2 && rm > 0 && ((st4[q4] == 4) ? 0 : max(lv4[q4], 1)) == m) {
+                        const int view = (int)(idx / un), v = (int)(idx % un);
+                        const size_t vb = (size_t)view * P.n;
+                        bool ok = true;
+                        // base neighbours, four at a time: ids first, then states and live counters together
+                        const int pb = __ldg(P.ptr + v), pe = __ldg(P.ptr + v + 1);
+                        for (int p = pb; p < pe && ok; p += 4) {
+                            int u4[4];
+#pragma unroll
+                            for (int k = 0; k < 4; k++) u4[k] = (p + k < pe) ? __ldg(P.col + p + k) : -1;
+                            uint8_t s4[4];
+                            int l4[4];
+#pragma unroll
+                            for (int k = 0; k < 4; k++) {
+                                s4[k] = 2; l4[k] = 0;
+                                if (u4[k] > v) { s4[k] = ldcg_u8(P.state + vb + u4[k]); l4[k] = ldcg_i32(P.live + vb + u4[k]); }
                             }
+#pragma unroll
+                            for (int k = 0; k < 4; k++)
+                                if (u4[k] > v && s4[k] != 2 && max(l4[k], 1) == m) ok = false;
+                        }
+                        const int4* pool = P.pool + (size_t)view * (size_t)P.pool_cap;
+                        for (int p = ldcg_i32(P.head + idx); p >= 0 && ok;) {
+                            int4 en = __ldcg(pool + p);
+                            if (en.x > v) {
+                                uint8_t su = ldcg_u8(P.state + vb + en.x);
+                                int lu = ldcg_i32(P.live + vb + en.x);
+                                if (su != 2 && max(lu, 1) == m) ok = false;
+                            }
+                            p = en.z;
+                        }
+                        cand = ok;
+                    }
+                    unsigned cm = __ballot_sync(RLAP_FULL_MASK, cand);
+                    if (cm == 0) continue;
+                    if (wfill + 32 > WBUF) flush();
+                    if (cand) {
+                        P.candround[idx] = rounds;
+                        wbuf[wfill + __popc(cm & lt)] = idx;
+                        if (bsm) {
+                            atomicAdd(scnt + seg, 1);
+                        } else {
+                            int c = atomicAdd(P.cntI + seg, 1);
+                            if (c + 1 > rm) P.ctr[CTR_OVF0 + par] = 1;
                         }
                     }
-                }
-                unsigned cm = __ballot_sync(RLAP_FULL_MASK, cand);
-                if (cm == 0) continue;
-                int leader = __ffs(cm) - 1;
-                int pos0 = 0;
-                if (lane == leader) pos0 = atomicAdd(P.ctr + rc.wslot, __popc(cm));
-                pos0 = __shfl_sync(RLAP_FULL_MASK, pos0, leader);
-                int seg0 = __shfl_sync(RLAP_FULL_MASK, seg, leader);
-                bool same = __all_sync(RLAP_FULL_MASK, !cand || seg == seg0);
-                if (cand) {
-                    P.candround[idx] = rounds;
-                    P.wl[rc.wl_base + pos0 + __popc(cm & lt)] = idx;
-                }
-                if (same) {
-                    if (lane == leader) {
-                        int c = atomicAdd(P.cntI + seg0, __popc(cm));
-                        if (c + __popc(cm) > rm) P.ctr[CTR_OVF0 + par] = 1;
-                    }
-                } else if (cand) {
-                    int c = atomicAdd(P.cntI + seg, 1);
-                    if (c + 1 > rm) P.ctr[CTR_OVF0 + par] = 1;
+                    wfill += __popc(cm);
                 }
             }
+            flush();
+            if (bsm) {
+                __syncthreads();
+                for (int q = threadIdx.x; q < (int)VG; q += blockDim.x) {
+                    int c = scnt[q];
+                    if (c > 0) {
+                        int c0 = atomicAdd(P.cntI + q, c);
+                        if (c0 + c > srem[q]) P.ctr[CTR_OVF0 + par] = 1;
+                    }
+                }
+            }
+            __syncthreads();   // the shared copies are star buffers again from here on
             grid.sync();
+            lap(ST_T_B);
             // phase C: a graph that selected more than it may still remove keeps its highest ids
             if (ldcg_i32(P.ctr + CTR_OVF0 + par)) {
                 const int gw = (int)(tid >> 5), nw = (int)(nthr >> 5), lane = threadIdx.x & 31;
@@ -825,6 +980,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
                     if (lane == 0) { P.thresh[s] = (unsigned int)T; P.ovfseg[s] = 1; }
                 }
                 grid.sync();
+                lap(ST_T_C);
             }
             // the truncated count is what phase D will eliminate
             for (long long q = tid; q < VG; q += nthr) {
@@ -836,11 +992,13 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
             run_warp_items(P, rc, smem, &cs, wl_start, wl_end, ls);
             wl_start = wl_end;
             grid.sync();
+            lap(ST_T_D1);
             int dl_end = dl_start + ldcg_i32(P.ctr + rc.dslot);
             if (dl_end != dl_start) {
                 run_block_items(P, rc, smem, &cs, dl_start, dl_end, ls);
                 dl_start = dl_end;
                 grid.sync();
+                lap(ST_T_D2);
             }
             rounds++;
         }

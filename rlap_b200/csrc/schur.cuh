@@ -39,7 +39,8 @@ struct RoundCtx {
     int dl_base;
     int dslot;
 };
-enum { ST_FILLS = 0, ST_POOL_MAX = 1, ST_MAXSTAR = 2, ST_DEFERRED = 3, ST_RAW = 4, ST_COUNT = 8 };
+enum { ST_FILLS = 0, ST_POOL_MAX = 1, ST_MAXSTAR = 2, ST_DEFERRED = 3, ST_RAW = 4,
+       ST_T_INIT = 8, ST_T_A = 9, ST_T_B = 10, ST_T_C = 11, ST_T_D1 = 12, ST_T_D2 = 13, ST_COUNT = 16 };
 
 struct SchurParams {
     // coalesced graph (shared by all views, immutable)

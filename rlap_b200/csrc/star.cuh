@@ -39,21 +39,12 @@ __device__ __forceinline__ StarBuf scratch_buf(const SchurParams& P) {
 // of every run keeps the summed fixed-point weight (and, if the run has more than one entry, the
 // dequantised fp32 weight); the others are marked dead (weight word RLAP_DEAD_W, Q = 0) but keep the
 // neighbour id. Returns the number of distinct neighbours; *P2_out = padded length.
+// merge the runs of equal neighbour of a star already sorted by A; Q is (re)computed here
 template <bool CTA>
-__device__ int star_sort_merge(StarBuf sb, int lraw, int shift, CtaScratch* cs, int* P2_out) {
+__device__ int star_merge_sorted(StarBuf sb, int lraw, int shift, CtaScratch* cs) {
     const int gs = g_size<CTA>(), r = g_rank<CTA>();
-    const int P2 = next_pow2(lraw);
-    for (int i = r; i < P2; i += gs) {
-        if (i < lraw) {
-            sb.Q[i] = quantize(a_w(sb.A[i]), shift);
-        } else {
-            sb.A[i] = RLAP_PAD_A;
-            sb.Q[i] = 0;
-        }
-        sb.K[i] = ~0ull;
-    }
+    for (int i = r; i < lraw; i += gs) sb.Q[i] = quantize(a_w(sb.A[i]), shift);
     g_sync<CTA>();
-    g_bitonic_sort<CTA, SORT_BY_A>(sb, P2);
     int L = 0;
     if (CTA) {
         if (threadIdx.x == 0) cs->icount = 0;
@@ -92,10 +83,22 @@ __device__ int star_sort_merge(StarBuf sb, int lraw, int shift, CtaScratch* cs, 
     g_sync<CTA>();
     if (CTA) L = cs->icount;
     g_sync<CTA>();
-    *P2_out = P2;
     return L;
 }
 
+template <bool CTA>
+__device__ int star_sort_merge(StarBuf sb, int lraw, int shift, CtaScratch* cs, int* P2_out) {
+    const int gs = g_size<CTA>(), r = g_rank<CTA>();
+    const int P2 = next_pow2(lraw);
+    for (int i = r; i < P2; i += gs) {
+        if (i >= lraw) { sb.A[i] = RLAP_PAD_A; sb.Q[i] = 0; }
+        sb.K[i] = ~0ull;
+    }
+    g_sync<CTA>();
+    g_bitonic_sort_keys<CTA>(sb.A, P2);
+    *P2_out = P2;
+    return star_merge_sorted<CTA>(sb, lraw, shift, cs);
+}
 
 // ---------------------------------------------------------------------------------------------
 // register-resident stars: one entry per lane
@@ -268,7 +271,8 @@ template <int W> struct Tile {
         return lo;
     }
     // merge runs of equal neighbour of a sorted tile star; see warp_merge_sorted
-    static __device__ __forceinline__ unsigned merge_sorted(uint64_t& a, unsigned long long& q, int& shift, bool need_q) {
+    static __device__ __forceinline__ unsigned merge_sorted(uint64_t& a, unsigned long long& q, int& shift, bool need_q,
+                                                            int& mult) {
         const int l = tl();
         const bool valid = a != RLAP_PAD_A;
         const uint32_t nb = a_nbr(a);
@@ -278,6 +282,7 @@ template <int W> struct Tile {
         const unsigned hmask = ballot(head);
         q = 0;
         shift = 0;
+        mult = valid ? 1 : 0;
         const bool dups = hmask != vmask;
         const bool anyd = __any_sync(RLAP_FULL_MASK, dups);   // keep the tiles of a warp in lock step
         uint32_t wmaxb = max_u32(valid ? (uint32_t)a : 0u);
@@ -299,6 +304,7 @@ template <int W> struct Tile {
             if (dups) {
                 if (head) {
                     q = qs;
+                    mult = cnt;
                     if (cnt > 1) a = ((uint64_t)nb << 32) | (uint64_t)__float_as_uint(dequantize(qs, shift));
                 } else if (valid) {
                     q = 0;
