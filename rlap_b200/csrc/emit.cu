@@ -123,15 +123,110 @@ __device__ void emit_sort_staged(const SchurParams& P, size_t idx, StarBuf sb, C
     g_sync<CTA>();
 }
 
+// A warp sorts one segment of up to 32 * R entries in registers (element e = r * 32 + lane), merges the runs of
+// equal neighbour with the fixed-point rule (segmented suffix sums over the register tile) and writes the
+// merged entries back to the start of the segment, neighbours ascending.
+template <int R>
+__device__ void emit_sort_regs(const SchurParams& P, size_t idx, int lv, long long off) {
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    uint64_t a[R];
+    uint32_t wmaxb = 0;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const int e = r * 32 + lane;
+        a[r] = e < lv ? P.raw[off + e] : RLAP_PAD_A;
+        if (e < lv) wmaxb = max(wmaxb, (uint32_t)a[r]);
+    }
+    warp_sort_regs<R>(a);
+    // heads of runs
+    unsigned headm[R];
+    bool anydup = false;
+    {
+        uint32_t carry = 0xffffffffu;   // neighbour id of element e - 1 for lane 0 (no vertex has this id)
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const uint32_t nb = a_nbr(a[r]);
+            uint32_t prev = __shfl_up_sync(RLAP_FULL_MASK, nb, 1);
+            if (lane == 0) prev = carry;
+            const bool valid = a[r] != RLAP_PAD_A;
+            const bool head = valid && prev != nb;
+            headm[r] = __ballot_sync(RLAP_FULL_MASK, head);
+            anydup |= (headm[r] != __ballot_sync(RLAP_FULL_MASK, valid));
+            carry = __shfl_sync(RLAP_FULL_MASK, nb, 31);
+        }
+    }
+    if (anydup) {
+        wmaxb = warp_max_u32(wmaxb);
+        const int shift = star_shift(__uint_as_float(wmaxb), lv);
+        unsigned long long qs[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) qs[r] = (a[r] != RLAP_PAD_A) ? quantize(a_w(a[r]), shift) : 0ull;
+        // segmented suffix sums: after the step with distance d, qs(e) covers the run members in [e, e + 2d).
+        // Rows are updated in ascending order, in place: a step only reads rows >= r that are still old.
+#pragma unroll
+        for (int d = 1; d < 32 * R; d <<= 1) {
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                unsigned long long oq;
+                uint32_t onb;
+                if (d < 32) {
+                    const int src = (lane + d) & 31;
+                    unsigned long long q0 = __shfl_sync(RLAP_FULL_MASK, qs[r], src);
+                    uint32_t n0 = __shfl_sync(RLAP_FULL_MASK, a_nbr(a[r]), src);
+                    unsigned long long q1 = 0;
+                    uint32_t n1 = 0xffffffffu;
+                    if (r + 1 < R) {
+                        q1 = __shfl_sync(RLAP_FULL_MASK, qs[r + 1], src);
+                        n1 = __shfl_sync(RLAP_FULL_MASK, a_nbr(a[r + 1]), src);
+                    }
+                    const bool wrap = lane + d >= 32;
+                    oq = wrap ? q1 : q0;
+                    onb = wrap ? n1 : n0;
+                } else {
+                    const int r2 = r + (d >> 5);
+                    oq = (r2 < R) ? qs[r2 < R ? r2 : 0] : 0ull;
+                    onb = (r2 < R) ? a_nbr(a[r2 < R ? r2 : 0]) : 0xffffffffu;
+                }
+                if (a[r] != RLAP_PAD_A && onb == a_nbr(a[r])) qs[r] += oq;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            if (a[r] == RLAP_PAD_A) continue;
+            const bool head = (headm[r] >> lane) & 1u;
+            if (!head) {
+                a[r] = ((uint64_t)a_nbr(a[r]) << 32) | (uint64_t)RLAP_DEAD_W;
+            } else {
+                // merged iff the next element (e + 1) exists and is not the head of a run
+                const int e1 = r * 32 + lane + 1;
+                bool merged = false;
+                if (e1 < lv) {
+                    const unsigned hm = (lane == 31) ? ((r + 1 < R) ? headm[r + 1 < R ? r + 1 : 0] : 1u) : (headm[r] >> (lane + 1));
+                    merged = (hm & 1u) == 0;
+                }
+                if (merged) a[r] = ((uint64_t)a_nbr(a[r]) << 32) | (uint64_t)__float_as_uint(dequantize(qs[r], shift));
+            }
+        }
+    }
+    int rowbase = 0;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const bool keep = a[r] != RLAP_PAD_A && !a_dead(a[r]);
+        if (keep) P.raw[off + rowbase + __popc(headm[r] & lt)] = a[r];
+        rowbase += __popc(headm[r]);
+    }
+    if (lane == 0) P.outcnt[idx] = rowbase;
+}
+
+constexpr int CAP_REGS = 512;   // largest segment sorted in registers
+
 __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_emit_sort_warp(SchurParams P) {
-    extern __shared__ __align__(16) uint64_t smem[];
-    __shared__ CtaScratch cs;
     const long long VN = (long long)P.V * P.n;
     const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
-    StarBuf sb = warp_buf(smem);
     for (long long base = gw * 32; base < VN; base += nw * 32) {
         const long long idx = base + lane;
         int lv = 0;
@@ -141,10 +236,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_emit_sort_warp(SchurParams
             off = P.rawoff[idx];
             if (lv == 0) P.outcnt[idx] = 0;
         }
-        if (lv > CAP_WARP) {
-            int pos = atomicAdd(P.ctr + CTR_EMIT_DL, 1);
-            P.dl[pos] = (unsigned int)idx;
-        }
+        bool defer = lv > CAP_REGS;
         // register path: one vertex at a time, all 32 lanes on its (contiguous) segment
         unsigned small = __ballot_sync(RLAP_FULL_MASK, lv > 0 && lv <= 32);
         uint64_t a_next = RLAP_PAD_A;
@@ -172,12 +264,30 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_emit_sort_warp(SchurParams
             if ((hmask >> lane) & 1u) P.raw[koff + __popc(hmask & lt)] = a;
             if (lane == 0) P.outcnt[base + k] = __popc(hmask);
         }
-        unsigned medium = __ballot_sync(RLAP_FULL_MASK, lv > 32 && lv <= CAP_WARP);
-        while (medium) {
-            const int k = __ffs(medium) - 1;
-            medium &= medium - 1;
-            emit_sort_staged<false>(P, (size_t)(base + k), sb, &cs);
+        if (lv > 32 && lv <= CAP_REGS) {
+            int pos = atomicAdd(P.ctr + CTR_EMIT_ML, 1);
+            P.wl[pos] = (unsigned int)idx;       // the work list is free once the elimination kernel has returned
         }
+        if (defer) {   // more than CAP_REGS entries: staged path, one block per segment
+            int pos = atomicAdd(P.ctr + CTR_EMIT_DL, 1);
+            P.dl[pos] = (unsigned int)idx;
+        }
+    }
+}
+
+// segments of 33..512 entries: one warp each, registers only
+__global__ void __launch_bounds__(256, 2) k_emit_sort_mid(SchurParams P) {
+    const int gw = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int nw = (int)(((long long)gridDim.x * blockDim.x) >> 5);
+    const int end = P.ctr[CTR_EMIT_ML];
+    for (int it = gw; it < end; it += nw) {
+        const unsigned int idx = P.wl[it];
+        const int lv = rawcnt_of(P)[idx];
+        const long long off = P.rawoff[idx];
+        if (lv <= 64) emit_sort_regs<2>(P, idx, lv, off);
+        else if (lv <= 128) emit_sort_regs<4>(P, idx, lv, off);
+        else if (lv <= 256) emit_sort_regs<8>(P, idx, lv, off);
+        else emit_sort_regs<16>(P, idx, lv, off);
     }
 }
 
@@ -253,12 +363,11 @@ cudaError_t launch_emit_count(const SchurParams& P, long long* total_dev, cudaSt
     static bool attr_done = false;
     const size_t smem = (size_t)3 * CAP_CTA * sizeof(uint64_t);
     if (!attr_done) {
-        cudaFuncSetAttribute(k_emit_sort_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(k_emit_sort_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_done = true;
     }
     const long long VN = (long long)P.V * P.n;
-    cudaError_t e = cudaMemsetAsync(P.ctr + CTR_EMIT_DL, 0, sizeof(int), stream);
+    cudaError_t e = cudaMemsetAsync(P.ctr + CTR_EMIT_DL, 0, 2 * sizeof(int), stream);
     if (e != cudaSuccess) return e;
     k_emit_prep<<<(unsigned)((VN + 255) / 256), 256, 0, stream>>>(P);
     e = launch_exclusive_scan<long long>(P.blk, VN, P.rawoff, P.blocksum, nullptr, stream);
@@ -273,7 +382,8 @@ cudaError_t launch_emit_count(const SchurParams& P, long long* total_dev, cudaSt
     int blocks = 0;
     e = eliminate_grid(&blocks);
     if (e != cudaSuccess) return e;
-    k_emit_sort_warp<<<blocks, BLOCK_THREADS, smem, stream>>>(P);
+    k_emit_sort_warp<<<blocks * 2, BLOCK_THREADS, 0, stream>>>(P);
+    k_emit_sort_mid<<<148 * 8, 256, 0, stream>>>(P);
     k_emit_sort_block<<<blocks, BLOCK_THREADS, smem, stream>>>(P);
     return launch_exclusive_scan<long long>(P.outcnt, VN, P.outoff, P.blocksum, total_dev, stream);
 }

@@ -29,7 +29,8 @@ enum {
     CTR_OVF0 = 9,        // degree mode: some segment selected more candidates than it may remove
     CTR_OVF1 = 10,
     CTR_ROUNDS = 11,
-    CTR_EMIT_DL = 12,    // emission: deferred list tail
+    CTR_EMIT_DL = 12,    // emission: deferred list tail (segments for the block path)
+    CTR_EMIT_ML = 13,    // emission: mid list tail (33..512 entries, register path of k_emit_sort_mid)
     CTR_COUNT = 16
 };
 

@@ -201,6 +201,45 @@ __device__ __forceinline__ int warp_upper_bound(unsigned long long C, int L, uns
 
 
 // ---------------------------------------------------------------------------------------------
+// a warp sorts 32 * R keys held in registers: element e = r * 32 + lane. Compare-exchange partners at
+// distance >= 32 live in the same lane (pure register work), closer ones are reached by shuffles.
+// No shared memory, no barriers.
+// ---------------------------------------------------------------------------------------------
+template <int R>
+__device__ __forceinline__ void warp_sort_regs(uint64_t (&a)[R]) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 2; k <= 32 * R; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= 32) {
+                const int jr = j >> 5;
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    if ((r & jr) == 0) {
+                        const int r2 = r | jr;
+                        const bool up = (((r << 5) & k) == 0);   // lane bits are below k's bit here
+                        const uint64_t x = a[r], y = a[r2];
+                        const bool sw = up ? (y < x) : (x < y);
+                        a[r] = sw ? y : x;
+                        a[r2] = sw ? x : y;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    const uint64_t o = __shfl_xor_sync(RLAP_FULL_MASK, a[r], j);
+                    const bool up = ((((r << 5) | lane) & k) == 0);
+                    const bool take_min = (((lane & j) == 0) == up);
+                    const bool lt = a[r] < o;
+                    a[r] = (take_min == lt) ? a[r] : o;
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // sub-warp tiles: W lanes (8, 16 or 32) hold one star; 32 / W stars per warp run in lock step
 // ---------------------------------------------------------------------------------------------
 template <int W> struct Tile {
