@@ -1,30 +1,35 @@
 import sys, time; sys.path.insert(0, '/root/repo')
 import numpy as np, torch
 import rlap_b200
-from rlap_b200 import graphs
-n=169343
+from rlap_b200 import graphs, ops
+n=169343; V=64
 ei = graphs.barabasi_albert(n,7,seed=0)
-eit = torch.from_numpy(ei).cuda()
-def timeit(fn, reps=3):
-    fn(); torch.cuda.synchronize()
-    ts=[]
-    for _ in range(reps):
-        a=torch.cuda.Event(enable_timing=True); b=torch.cuda.Event(enable_timing=True)
-        a.record(); fn(); b.record(); torch.cuda.synchronize(); ts.append(a.elapsed_time(b))
-    return min(ts)
-if len(sys.argv) > 1:
-    ov, V = sys.argv[1], int(sys.argv[2])
-    g = rlap_b200.prepare(eit, None, n)
-    for _ in range(2):
-        out,vp,s = rlap_b200.schur_views(g, n//2, ov, "asc", num_views=V, seed=1, dtype=None, return_stats=True)
-    torch.cuda.synchronize(); print(s); sys.exit(0)
-print("ingest ms", timeit(lambda: rlap_b200.prepare(eit, None, n)))
-g = rlap_b200.prepare(eit, None, n)
-for ov,on in [("degree","asc"),("coarsen","asc"),("random","asc")]:
-    for V in [1,4,16,64]:
-        st={}
-        def f():
-            out,vp,s = rlap_b200.schur_views(g, n//2, ov, on, num_views=V, seed=1, dtype=None, return_stats=True)
-            st.update(s)
-        ms = timeit(f, reps=2)
-        print(f"{ov}/{on} V={V}: {ms:.2f} ms -> {V/ms*1e3:.1f} views/s  rounds {st['rounds']} maxstar {st['max_star']} elim {st['elim_us']/1e3:.2f} ms emitcount {st['emit_count_us']/1e3:.2f} ms", flush=True)
+dev=torch.device('cuda',0)
+ei_pinned = torch.from_numpy(ei).pin_memory()
+copy_stream = torch.cuda.Stream(device=dev)
+hb=[None,None]; pend=[None,None]
+T=time.perf_counter
+for step in range(8):
+    t0=T()
+    slot=step&1
+    if pend[slot] is not None: pend[slot].synchronize()
+    t1=T()
+    d = ei_pinned.to(dev, non_blocking=True)
+    g = ops.prepare(d, None, n)
+    t2=T()
+    (row,col,w),vp = ops.schur_views(g, n//2, "degree","asc", num_views=V, seed=step, dtype=None)
+    t3=T()
+    total=int(vp[-1])
+    if hb[slot] is None:
+        cap=int(total*1.05); hb[slot]=[torch.empty(cap,dtype=torch.int32).pin_memory(), torch.empty(cap,dtype=torch.int32).pin_memory(), torch.empty(cap,dtype=torch.float32).pin_memory()]
+    t4=T()
+    ready=torch.cuda.Event(); ready.record()
+    with torch.cuda.stream(copy_stream):
+        copy_stream.wait_event(ready)
+        for h,x in zip(hb[slot],(row,col,w)):
+            h[:total].copy_(x, non_blocking=True); x.record_stream(copy_stream)
+        done=torch.cuda.Event(); done.record()
+    pend[slot]=done
+    t5=T()
+    print(f"step {step}: wait {1e3*(t1-t0):.1f} prepare {1e3*(t2-t1):.1f} views {1e3*(t3-t2):.1f} alloc {1e3*(t4-t3):.1f} enqueue {1e3*(t5-t4):.1f} ms", flush=True)
+torch.cuda.synchronize()
