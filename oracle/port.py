@@ -42,6 +42,7 @@ def lib():
             ctypes.c_int64, P, P, P, ctypes.c_int64, P, P, ctypes.c_int, ctypes.c_int, ctypes.c_uint64,
             ctypes.c_uint32, ctypes.c_int, P, P, P, ctypes.c_int64, P, P]
         L.oracle_keyed_schur.restype = ctypes.c_int64
+        L.oracle_ref_random_order.argtypes = [ctypes.c_int64, ctypes.c_uint64, P]
         L.oracle_rank_perm.argtypes = [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, P]
         _lib = L
     return _lib
@@ -73,6 +74,13 @@ def philox(k0, k1, c0, c1, c2, c3):
 def rank_perm(seed, graph, view, n_g):
     out = np.zeros(n_g, dtype=np.uint32)
     lib().oracle_rank_perm(seed, graph, view, n_g, out.ctypes.data)
+    return out
+
+
+def ref_random_order(n, rd_seed):
+    """elimination (pop) order of the reference's random queue for the injected random_device stream"""
+    out = np.zeros(n, dtype=np.int64)
+    lib().oracle_ref_random_order(n, rd_seed, out.ctypes.data)
     return out
 
 

@@ -790,3 +790,14 @@ extern "C" void oracle_rank_perm(uint64_t seed, uint32_t graph, uint32_t view, u
     keyed::RankPerm rp(ph, graph, view, n_g);
     for (uint32_t v = 0; v < n_g; v++) out[v] = rp.rank(v);
 }
+
+// The pop order of the reference's o_v = random queue for a given injected random_device stream
+// (preconditioner.cc:588-613: shuffle 0..n-1 with mt19937(rd()), pop from the back). Test helper.
+extern "C" void oracle_ref_random_order(int64_t n, uint64_t rd_state, int64_t* out) {
+    refmode::RdStream rd{rd_state};
+    std::vector<double> node_id((size_t)n);
+    for (int64_t i = 0; i < n; i++) node_id[(size_t)i] = (double)i;
+    std::mt19937 g(rd.next());
+    std::shuffle(node_id.begin(), node_id.end(), g);
+    for (int64_t i = 0; i < n; i++) out[i] = (int64_t)node_id[(size_t)(n - 1 - i)];
+}
