@@ -30,6 +30,8 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <cstdio>
+#include <limits>
 #include <random>
 #include <string>
 #include <vector>
@@ -547,6 +549,7 @@ static void gather_star(const Graph& g, int32_t i, Star& s) {
         mm.nbr = raw[p].nbr;
         mm.q = q;
         mm.wf = (e - p == 1) ? raw[p].w : (float)std::ldexp((double)q, -s.shift);
+        if (!(mm.wf > 0.0f)) mm.wf = std::numeric_limits<float>::denorm_min();   // a merged edge never vanishes on one side
         mm.shuf = 0; mm.usample = 0;
         s.m.push_back(mm);
         s.S += q;
@@ -554,11 +557,21 @@ static void gather_star(const Graph& g, int32_t i, Star& s) {
     }
 }
 
+// o_n order of the merged neighbours. Ties (the rule, not the exception: every call site of the reference uses unit
+// weights) are broken the way the reference's std::sort leaves them: libstdc++ sorts up to 16 elements with a
+// stable insertion sort, so equal weights keep their neighbour-id order (the column was sorted by row just before,
+// preconditioner.cc:275-276, 295-303); above 16 elements introsort leaves an arbitrary order, restated here as the
+// order of the per-neighbour Philox key.
 static void order_star(Star& s, int o_n) {
+    const bool hashed = s.m.size() > 16;
+    auto tie = [hashed](const Merged& a, const Merged& b) {
+        if (hashed && a.shuf != b.shuf) return a.shuf < b.shuf;
+        return a.nbr < b.nbr;
+    };
     if (o_n == ON_ASC)
-        std::sort(s.m.begin(), s.m.end(), [](const Merged& a, const Merged& b) { return a.q != b.q ? a.q < b.q : a.nbr < b.nbr; });
+        std::sort(s.m.begin(), s.m.end(), [&](const Merged& a, const Merged& b) { return a.q != b.q ? a.q < b.q : tie(a, b); });
     else if (o_n == ON_DESC)
-        std::sort(s.m.begin(), s.m.end(), [](const Merged& a, const Merged& b) { return a.q != b.q ? a.q > b.q : a.nbr < b.nbr; });
+        std::sort(s.m.begin(), s.m.end(), [&](const Merged& a, const Merged& b) { return a.q != b.q ? a.q > b.q : tie(a, b); });
     else
         std::sort(s.m.begin(), s.m.end(), [](const Merged& a, const Merged& b) { return a.shuf != b.shuf ? a.shuf < b.shuf : a.nbr < b.nbr; });
 }
@@ -631,6 +644,7 @@ static void eliminate(Graph& g, int32_t i, int o_v, int o_n, int flags, const Ph
         double t1 = (double)mj.wf * (double)rem;
         float w = (float)(t1 / (double)s.S);
         if (w > 0) { add_edge(g, mj.nbr, s.m[(size_t)koff].nbr, w); st.F++; }
+        else if (getenv("ORACLE_TRACE")) fprintf(stderr, "oracle: underflow at i=%d L=%lld lraw=%lld j=%d (pos %lld) k=%d wf=%g rem=%llu S=%llu\n", i, (long long)L, (long long)s.lraw, mj.nbr, (long long)j, s.m[(size_t)koff].nbr, (double)mj.wf, (unsigned long long)rem, (unsigned long long)s.S);
     }
 }
 

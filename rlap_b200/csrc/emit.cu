@@ -11,6 +11,7 @@
 //                   (<= 32 entries: warp shuffles in registers; <= 128: warp + smem; else thread block)
 //                                                       -> scan -> outoff
 //   k_emit_copy     compact copy into the caller's buffers (packed and/or [E',3] float64)
+#include <stdlib.h>
 #include "rlap_device.cuh"
 #include "schur.cuh"
 #include "scan.cuh"
@@ -62,6 +63,18 @@ __global__ void __launch_bounds__(256) k_emit_scatter(SchurParams P) {
     for (long long e = t0; e < used; e += nt) {
         int4 en = pool[e];
         if (en.w >= 0) scatter_one(P, vb, en.w, en.x, (uint32_t)en.y);
+    }
+}
+
+// debug (RLAP_DEBUG_CHECK=1): every survivor's scattered entry count must equal its live counter
+__global__ void k_emit_check(SchurParams P) {
+    const long long VN = (long long)P.V * P.n;
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= VN) return;
+    int c = cursor_of(P)[idx], rc = rawcnt_of(P)[idx];
+    if (c != rc) {
+        atomicAdd(P.stats + 7, 1ull);
+        atomicMax(P.stats + 6, ((unsigned long long)(unsigned)idx << 32) | ((unsigned long long)(unsigned)(c & 0xffff) << 16) | (unsigned)(rc & 0xffff));
     }
 }
 
@@ -205,7 +218,7 @@ __device__ void emit_sort_regs(const SchurParams& P, size_t idx, int lv, long lo
                     const unsigned hm = (lane == 31) ? ((r + 1 < R) ? headm[r + 1 < R ? r + 1 : 0] : 1u) : (headm[r] >> (lane + 1));
                     merged = (hm & 1u) == 0;
                 }
-                if (merged) a[r] = ((uint64_t)a_nbr(a[r]) << 32) | (uint64_t)__float_as_uint(dequantize(qs[r], shift));
+                if (merged) a[r] = ((uint64_t)a_nbr(a[r]) << 32) | (uint64_t)__float_as_uint(dequantize_merged(qs[r], shift));
             }
         }
     }
@@ -379,6 +392,7 @@ cudaError_t launch_emit_count(const SchurParams& P, long long* total_dev, cudaSt
         if (bx > 148 * 8) bx = 148 * 8;
         k_emit_scatter<<<dim3((unsigned)bx, (unsigned)P.V), 256, 0, stream>>>(P);
     }
+    if (getenv("RLAP_DEBUG_CHECK")) k_emit_check<<<(unsigned)((VN + 255) / 256), 256, 0, stream>>>(P);
     int blocks = 0;
     e = eliminate_grid(&blocks);
     if (e != cudaSuccess) return e;

@@ -89,6 +89,14 @@ __device__ __forceinline__ float dequantize(unsigned long long q, int shift) {
     return __double2float_rn(__dmul_rn(__ull2double_rn(q), pow2d(-shift)));
 }
 
+// fp32 weight of a merged multi-edge. Never zero: with a dynamic range beyond 2^38 inside one star the sum could
+// round to 0 on one endpoint's side only and the edge would lose one direction at the next ingest (zero weights
+// are dropped, reader.cc:50); the smallest positive float keeps both directions.
+__device__ __forceinline__ float dequantize_merged(unsigned long long q, int shift) {
+    float w = dequantize(q, shift);
+    return w > 0.f ? w : __uint_as_float(1u);
+}
+
 __device__ __forceinline__ uint64_t pack_a(uint32_t nbr, float w) {
     return ((uint64_t)nbr << 32) | (uint64_t)__float_as_uint(w);
 }
@@ -193,8 +201,10 @@ __device__ __forceinline__ bool rec_less(uint64_t a1, uint64_t q1, uint64_t k1, 
     bool d1 = a_dead(a1), d2 = a_dead(a2);
     if (d1 != d2) return d2;
     if (d1) return a1 < a2;
-    if (MODE == SORT_ASC) return (q1 != q2) ? (q1 < q2) : (a1 < a2);
-    if (MODE == SORT_DESC) return (q1 != q2) ? (q1 > q2) : (a1 < a2);
+    // asc / desc: ties by the secondary key K (equal for all entries of a star with <= 16 neighbours, the
+    // per-neighbour Philox key above: DESIGN.md §3.3), then by neighbour id
+    if (MODE == SORT_ASC && q1 != q2) return q1 < q2;
+    if (MODE == SORT_DESC && q1 != q2) return q1 > q2;
     return (k1 != k2) ? (k1 < k2) : (a1 < a2);
 }
 
@@ -210,11 +220,11 @@ __device__ __forceinline__ void g_bitonic_sort(StarBuf sb, int P) {
                 int l = i | j;
                 bool up = ((i & k) == 0);
                 uint64_t a1 = sb.A[i], a2 = sb.A[l], q1 = sb.Q[i], q2 = sb.Q[l];
-                uint64_t k1 = (MODE == SORT_KEY) ? sb.K[i] : 0, k2 = (MODE == SORT_KEY) ? sb.K[l] : 0;
+                uint64_t k1 = (MODE != SORT_BY_A) ? sb.K[i] : 0, k2 = (MODE != SORT_BY_A) ? sb.K[l] : 0;
                 bool sw = up ? rec_less<MODE>(a2, q2, k2, a1, q1, k1) : rec_less<MODE>(a1, q1, k1, a2, q2, k2);
                 if (sw) {
                     sb.A[i] = a2; sb.A[l] = a1; sb.Q[i] = q2; sb.Q[l] = q1;
-                    if (MODE == SORT_KEY) { sb.K[i] = k2; sb.K[l] = k1; }
+                    if (MODE != SORT_BY_A) { sb.K[i] = k2; sb.K[l] = k1; }
                 }
             }
             g_sync<CTA>();

@@ -188,7 +188,7 @@ __device__ void eliminate_star(const SchurParams& P, const RoundCtx& rc, int vie
         const bool full = (P.flags & 1) != 0;
         const bool coarsen = (P.o_v == 2) && !full;
         const int on = coarsen ? 2 : P.o_n;
-        if (!full && on == 2) {
+        if (!full && (on == 2 || L > 16)) {   // shuffle key; for asc / desc the tie-break of stars with > 16 neighbours
             for (int i = r; i < lraw; i += gs) {
                 uint64_t a = sb.A[i];
                 if (!a_dead(a)) {
@@ -347,19 +347,23 @@ __device__ bool eliminate_star_tile(const SchurParams& P, const RoundCtx& rc, un
     const bool full = (P.flags & 1) != 0;
     const bool coarsen = (P.o_v == 2) && !full;
     const int on = coarsen ? 2 : P.o_n;
-    uint64_t key = ~0ull;
+    uint64_t key = ~0ull, tie = 0;
     if (live) {
-        if (full || on == 0) key = q;
-        else if (on == 1) key = ~q;
-        else {
+        uint64_t shuf = 0;
+        if (!full && (on == 2 || (W == 32 && L > 16))) {
             uint4 x = philox4x32_10(P.k0, P.k1, (uint32_t)v, a_nbr(a), view_id, TAG_STAR);
-            key = ((uint64_t)x.z << 32) | (uint64_t)x.w;
+            shuf = ((uint64_t)x.z << 32) | (uint64_t)x.w;
         }
+        if (full || on == 0) { key = q; tie = shuf; }
+        else if (on == 1) { key = ~q; tie = shuf; }
+        else key = shuf;
     } else {
         a = RLAP_PAD_A;
         q = 0;
+        tie = ~0ull;   // padding sorts after every live entry, also after one whose key is ~0 (q = 0 under desc)
     }
-    T::sort_kaq(key, a, q);
+    if (W == 32) T::sort_ktaq(key, tie, a, q);   // only a 32-lane tile can hold more than 16 neighbours
+    else T::sort_kaq(key, a, q);
     const unsigned long long C = T::incl_scan(q);
     const unsigned long long S = __shfl_sync(RLAP_FULL_MASK, C, (L > 0 ? L - 1 : 0), W);
     const long long nf = (L < 1) ? 0 : (full ? (long long)L * (L - 1) / 2 : (long long)(L - 1));
@@ -511,6 +515,7 @@ __device__ void run_warp_items(const SchurParams& P, const RoundCtx& rc, uint64_
                 int nb = __ldg(P.ptr + v + 1) - __ldg(P.ptr + v);
                 if (lv <= CAP_WARP) cls = max(lv, nb);
                 else cls = lv;
+                if ((P.flags & 64) && lv <= CAP_WARP) cls = 33;   // debug: no register tiles
             }
         }
         if (lv > CAP_WARP) {

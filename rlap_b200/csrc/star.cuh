@@ -68,7 +68,7 @@ __device__ int star_merge_sorted(StarBuf sb, int lraw, int shift, CtaScratch* cs
         if (act) {
             if (headf) {
                 sb.Q[i] = qs;
-                if (c > 1) sb.A[i] = ((uint64_t)nb << 32) | (uint64_t)__float_as_uint(dequantize(qs, shift));
+                if (c > 1) sb.A[i] = ((uint64_t)nb << 32) | (uint64_t)__float_as_uint(dequantize_merged(qs, shift));
             } else {
                 sb.Q[i] = 0;
                 sb.A[i] = ((uint64_t)nb << 32) | (uint64_t)RLAP_DEAD_W;
@@ -155,7 +155,7 @@ __device__ __forceinline__ unsigned warp_merge_sorted(uint64_t& a, unsigned long
         }
         if (head) {
             q = qs;
-            if (cnt > 1) a = ((uint64_t)nb << 32) | (uint64_t)__float_as_uint(dequantize(qs, shift));
+            if (cnt > 1) a = ((uint64_t)nb << 32) | (uint64_t)__float_as_uint(dequantize_merged(qs, shift));
         } else if (valid) {
             q = 0;
             a = ((uint64_t)nb << 32) | (uint64_t)RLAP_DEAD_W;
@@ -281,6 +281,27 @@ template <int W> struct Tile {
             }
         }
     }
+    // same with a secondary key t between k and a
+    static __device__ __forceinline__ void sort_ktaq(uint64_t& k, uint64_t& t, uint64_t& a, unsigned long long& q) {
+        const int l = tl();
+#pragma unroll
+        for (int kk = 2; kk <= W; kk <<= 1) {
+#pragma unroll
+            for (int j = kk >> 1; j > 0; j >>= 1) {
+                uint64_t ok = __shfl_xor_sync(RLAP_FULL_MASK, k, j, W);
+                uint64_t ot = __shfl_xor_sync(RLAP_FULL_MASK, t, j, W);
+                uint64_t oa = __shfl_xor_sync(RLAP_FULL_MASK, a, j, W);
+                unsigned long long oq = __shfl_xor_sync(RLAP_FULL_MASK, q, j, W);
+                bool take_min = (((l & j) == 0) == ((l & kk) == 0));
+                bool lt = (k != ok) ? (k < ok) : ((t != ot) ? (t < ot) : (a < oa));
+                bool keep = (take_min == lt);
+                k = keep ? k : ok;
+                t = keep ? t : ot;
+                a = keep ? a : oa;
+                q = keep ? q : oq;
+            }
+        }
+    }
     static __device__ __forceinline__ uint32_t max_u32(uint32_t v) {
 #pragma unroll
         for (int d = W / 2; d > 0; d >>= 1) v = max(v, __shfl_xor_sync(RLAP_FULL_MASK, v, d, W));
@@ -344,7 +365,7 @@ template <int W> struct Tile {
                 if (head) {
                     q = qs;
                     mult = cnt;
-                    if (cnt > 1) a = ((uint64_t)nb << 32) | (uint64_t)__float_as_uint(dequantize(qs, shift));
+                    if (cnt > 1) a = ((uint64_t)nb << 32) | (uint64_t)__float_as_uint(dequantize_merged(qs, shift));
                 } else if (valid) {
                     q = 0;
                     a = ((uint64_t)nb << 32) | (uint64_t)RLAP_DEAD_W;

@@ -125,6 +125,7 @@ def schur_views(graph: Graph, num_remove, o_v: str, o_n: str, num_views: int = 1
     if seed is None:
         seed = _next_seed()
     flags = (_native.FLAG_FULL_CLIQUE if full_clique else 0) | (_native.FLAG_SHARED_ORDER if shared_order else 0)
+    flags |= int(__import__('os').environ.get('RLAP_DEBUG_FLAGS', '0'))
     V = int(num_views)
     if full_clique:  # test mode: cliques instead of trees, multi-edges pile up until a vertex goes
         pool_cap = pool_cap or 8 * graph.nnz + 4096
