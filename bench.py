@@ -320,6 +320,14 @@ def run_ours(args):
     path_bytes = 20.0 * E + 4.0 * N_NODES + alg_bytes + 24.0 * rows
     path_gbs = path_bytes / (ms_step * 1e-3) / 1e9
 
+    # measured DRAM traffic of the same kernel from the committed ncu --set full capture (same workload and V)
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_k_eliminate_traffic.json")))
+        if int(tj.get("views_per_launch", 0)) == V:
+            traffic = float(tj["traffic_bytes_per_launch"])
+    except Exception:
+        pass
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -335,7 +343,7 @@ def run_ours(args):
                 "api": "ops.prepare + ops.schur_views from pinned host edge_index; packed rows copied back to pinned host on a copy stream, overlapping the next step (2 buffer sets)"},
         "gpu_launches": int(n_launch),
         "roofline": {"bound": "hbm", "kernel": "k_eliminate", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": elim_us / 1e3,
                      "kernel_share_of_step": elim_us / 1e3 / ms_step,
                      "emit_count_ms": count_us / 1e3,
