@@ -92,7 +92,8 @@ int rlap_schur_eliminate(int64_t n, int64_t nnz, const int32_t* csr_ptr, const i
  * [4] raw adjacency entries read at elimination, [5] output rows, [6] pool_cap used,
  * [7] elimination kernel time (us, CUDA events), [8] emission count pass time (us),
  * [9..14] time inside the elimination kernel (us): init, min-key scan, candidate selection, truncation,
- * warp-level elimination, block-level elimination. */
+ * warp-level elimination, block-level elimination; [15] (only with RLAP_DEBUG_CHECK=1 in the environment) number of
+ * surviving vertices whose scattered entry count differs from their live counter: must be 0. */
 
 /* ---- emission (replaces the output assembly, preconditioner.cc:435-457 / 789-810 / 916-934) ------
  * Writes the rows of all views back to back, view after view, each view sorted by (col, row):

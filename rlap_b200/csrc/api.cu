@@ -392,7 +392,6 @@ int rlap_schur_eliminate(int64_t n, int64_t nnz, const int32_t* csr_ptr, const i
         stats[8] = (int64_t)(ms_count * 1000.0f);  // emission count pass + scan, microseconds
         for (int i = 0; i < 6; i++) stats[9 + i] = (int64_t)(hstats[ST_T_INIT + i] / 1000);  // phase times, us
         stats[15] = (int64_t)hstats[7];  // debug check: vertices whose scattered count != live counter
-        stats[7 + 0] = stats[7];
         if (hstats[7]) fprintf(stderr, "rlap debug: %llu live/scatter mismatches, last idx %llu scattered %llu live %llu\n", hstats[7], hstats[6] >> 32, (hstats[6] >> 16) & 0xffff, hstats[6] & 0xffff);
     }
     {

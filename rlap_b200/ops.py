@@ -171,7 +171,7 @@ def schur_views(graph: Graph, num_remove, o_v: str, o_n: str, num_views: int = 1
     if return_stats:
         names = ["rounds", "fills", "pool_used_max", "max_star", "raw_entries_read", "rows", "pool_cap", "elim_us",
                  "emit_count_us", "t_init_us", "t_phaseA_us", "t_phaseB_us", "t_phaseC_us", "t_elim_warp_us",
-                 "t_elim_block_us"]
+                 "t_elim_block_us", "check_mismatches"]
         return out, view_ptr, dict(zip(names, (int(x) for x in stats)))
     return out, view_ptr
 
