@@ -353,6 +353,10 @@ int rlap_schur_eliminate(int64_t n, int64_t nnz, const int32_t* csr_ptr, const i
     if (!ev[0]) for (int i = 0; i < 3; i++) CK(cudaEventCreate(&ev[i]));
     CK(cudaEventRecord(ev[0], stream));
     CK(launch_eliminate(P, stream));
+    if (getenv("RLAP_DEBUG_SYNC")) {
+        cudaError_t de = cudaStreamSynchronize(stream);
+        if (de != cudaSuccess) return cuda_fail(de, "k_eliminate (debug sync)");
+    }
     CK(cudaEventRecord(ev[1], stream));
     CK(launch_emit_count(P, L.total_dev, stream));
     CK(cudaEventRecord(ev[2], stream));

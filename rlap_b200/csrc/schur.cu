@@ -464,22 +464,26 @@ __device__ unsigned run_tier(const SchurParams& P, const RoundCtx& rc, unsigned 
     const int tile = lane / W;
     unsigned failed = 0;
     while (mask) {
-        // tile t takes the t-th pending item
-        unsigned src = __fns(mask, 0, tile + 1);            // lane holding that item, 0xffffffff if none
+        // tile t takes the t-th pending item (lowest set bits first)
+        unsigned rest = mask;
+        unsigned src = 0xffffffffu;
+        unsigned took[TPW];
+#pragma unroll
+        for (int t = 0; t < TPW; t++) {
+            took[t] = rest ? (unsigned)(__ffs(rest) - 1) : 0xffffffffu;
+            if (t == tile) src = took[t];
+            rest &= rest - 1;          // 0 & anything stays 0
+        }
         unsigned int idx = __shfl_sync(RLAP_FULL_MASK, my_idx, src & 31);
         long long sl0 = __shfl_sync(RLAP_FULL_MASK, my_slot0, src & 31);
         int nsl = __shfl_sync(RLAP_FULL_MASK, my_nslots, src & 31);
         if (src == 0xffffffffu) idx = 0xffffffffu;
         bool f = eliminate_star_tile<W>(P, rc, idx, sl0, nsl, ls);
         unsigned fm = __ballot_sync(RLAP_FULL_MASK, f && (lane & (W - 1)) == 0);
-        // translate failing tiles back to item bits and drop the processed items from the mask
 #pragma unroll
-        for (int t = 0; t < TPW; t++) {
-            unsigned s = __fns(mask, 0, 1);
-            if (s == 0xffffffffu) break;
-            if ((fm >> (t * W)) & 1u) failed |= 1u << s;
-            mask &= mask - 1;
-        }
+        for (int t = 0; t < TPW; t++)
+            if (took[t] != 0xffffffffu && ((fm >> (t * W)) & 1u)) failed |= 1u << took[t];
+        mask = rest;
     }
     return failed;
 }
@@ -758,6 +762,9 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
                 bool any = false;
                 // four independent elements per thread and iteration; every load is issued before the first use,
                 // so one memory round trip serves four vertices
+                // (view, vertex) of the running index are advanced incrementally: no division in the loop
+                const unsigned step_q = (unsigned)nthr / un, step_r = (unsigned)nthr % un;
+                unsigned cview = (unsigned)tid / un, cv = (unsigned)tid % un;
                 for (unsigned base = (unsigned)(tid - lane); base < uVN; base += 4u * (unsigned)nthr) {
                     uint8_t st4[4];
                     int lv4[4], rm4[4], sg4[4];
@@ -765,8 +772,10 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
                     for (int q4 = 0; q4 < 4; q4++) {
                         const unsigned idx = base + (unsigned)q4 * (unsigned)nthr + lane;
                         st4[q4] = 2; lv4[q4] = 0; rm4[q4] = 0; sg4[q4] = 0;
+                        const int view = (int)cview, v = (int)cv;
+                        cview += step_q; cv += step_r;
+                        if (cv >= un) { cv -= un; cview++; }
                         if (idx < uVN) {
-                            int view = (int)(idx / un), v = (int)(idx % un);
                             sg4[q4] = view * P.G + graph_of(P, v);
                             st4[q4] = ldcg_u8(P.state + idx);
                             lv4[q4] = ldcg_i32(P.live + idx);
@@ -832,15 +841,20 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
                 __syncwarp();
                 wfill = 0;
             };
+            const unsigned step_q = (unsigned)nthr / un, step_r = (unsigned)nthr % un;
+            unsigned cview = (unsigned)tid / un, cv = (unsigned)tid % un;
             for (unsigned base = (unsigned)(tid - lane); base < uVN; base += 4u * (unsigned)nthr) {
                 uint8_t st4[4];
-                int lv4[4], rm4[4], sg4[4], mk4[4];
+                int lv4[4], rm4[4], sg4[4], mk4[4], vw4[4], vx4[4];
 #pragma unroll
                 for (int q4 = 0; q4 < 4; q4++) {
                     const unsigned idx = base + (unsigned)q4 * (unsigned)nthr + lane;
                     st4[q4] = 2; lv4[q4] = 0; rm4[q4] = 0; sg4[q4] = 0; mk4[q4] = -1;
+                    const int view = (int)cview, v = (int)cv;
+                    vw4[q4] = view; vx4[q4] = v;
+                    cview += step_q; cv += step_r;
+                    if (cv >= un) { cv -= un; cview++; }
                     if (idx < uVN) {
-                        int view = (int)(idx / un), v = (int)(idx % un);
                         sg4[q4] = view * P.G + graph_of(P, v);
                         st4[q4] = ldcg_u8(P.state + idx);
                         lv4[q4] = ldcg_i32(P.live + idx);
@@ -854,7 +868,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
                     const int seg = sg4[q4], rm = rm4[q4], m = mk4[q4];
                     bool cand = false;
                     if (st4[q4] != 2 && rm > 0 && ((st4[q4] == 4) ? 0 : max(lv4[q4], 1)) == m) {
-                        const int view = (int)(idx / un), v = (int)(idx % un);
+                        const int view = vw4[q4], v = vx4[q4];
                         const size_t vb = (size_t)view * P.n;
                         bool ok = true;
                         // base neighbours, four at a time: ids first, then states and live counters together
