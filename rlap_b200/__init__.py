@@ -8,3 +8,9 @@ from .ops import (Graph, approximate_cholesky, approximate_cholesky_batched, ide
                   schur_views)
 
 VERSION = "0.1.0"
+
+
+def register_torch_op():
+    """register torch.ops.extension_cpp.approximate_cholesky / identity with the reference's schema"""
+    from . import torch_op
+    return torch_op.register()

@@ -185,3 +185,22 @@ def test_live_counters_are_exact(monkeypatch):
             for o_v, o_n in util.COMBOS:
                 _, _, st = rlap_b200.schur_views(g, t, o_v, o_n, num_views=4, seed=3, dtype=None, return_stats=True)
                 assert st["check_mismatches"] == 0, (name, o_v, o_n)
+
+
+def test_torch_dispatcher_op_schema():
+    """torch.ops.extension_cpp.approximate_cholesky keeps the reference's schema (py_api_binder.cc:80-83) and
+    dispatches on CUDA and CPU tensors"""
+    import rlap_b200
+    from rlap_b200 import graphs
+    assert rlap_b200.register_torch_op()
+    ei = graphs.barabasi_albert(100, 50, seed=0)
+    info = torch.from_numpy(util.edge_info(ei))
+    for t in (info, info.cuda()):
+        out = torch.ops.extension_cpp.approximate_cholesky.default(edge_info=t, num_nodes=100, num_remove=50,
+                                                                   o_v="random", o_n="asc")
+        assert out.dtype == torch.double and out.shape[1] == 3 and out.device == t.device
+        assert torch.unique(out[:, :2]).numel() == 50
+    a = torch.randn(8, 8, dtype=torch.double)
+    assert torch.equal(torch.ops.extension_cpp.identity.default(a=a), a)
+    schema = str(torch.ops.extension_cpp.approximate_cholesky.default._schema)
+    assert "Tensor edge_info, int num_nodes, int num_remove, str o_v, str o_n" in schema
