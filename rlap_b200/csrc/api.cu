@@ -22,7 +22,6 @@ cudaError_t launch_setup_graphs(int n, int G, const int* gptr, const long long* 
 cudaError_t eliminate_grid(int* blocks_out);
 cudaError_t launch_eliminate(const SchurParams& P, cudaStream_t stream);
 cudaError_t launch_emit_count(const SchurParams& P, long long* total_dev, cudaStream_t stream);
-cudaError_t launch_rowid(int n, long long nnz, const int* ptr, int* rowid, cudaStream_t stream);
 cudaError_t launch_emit_write(const SchurParams& P, int* out_row, int* out_col, float* out_w, double* out_f64,
                               cudaStream_t stream);
 }  // namespace rlap
@@ -214,7 +213,6 @@ struct SchurLayout {
     int* teff_dev;
     long long* total_dev;
     long long* viewptr_dev;   // [V+1]
-    int* rowid_dev;
     long long G, V, pool_cap, scratch_cap;
 };
 
@@ -256,8 +254,6 @@ static SchurLayout schur_layout(long long n, long long nnz, long long G, long lo
     P.outcnt = c.take<int>(VN);
     P.outoff = c.take<long long>(VN + 1);
     P.rawoff = c.take<long long>(VN + 1);
-    L.rowid_dev = c.take<int>((size_t)nnz + 1);
-    P.rowid = L.rowid_dev;
     // live entries never exceed the input's outside full-clique mode; the full-clique
     // test mode may keep every pool entry alive as well
     P.raw_cap = (long long)V * (nnz + (full_clique ? pool_cap : 0)) + 1;
@@ -345,7 +341,6 @@ int rlap_schur_eliminate(int64_t n, int64_t nnz, const int32_t* csr_ptr, const i
     }
     CK(cudaMemsetAsync(P.ctr, 0, sizeof(int) * CTR_COUNT, stream));
     CK(cudaMemsetAsync(P.stats, 0, sizeof(unsigned long long) * ST_COUNT, stream));
-    CK(launch_rowid((int)n, nnz, csr_ptr, L.rowid_dev, stream));
     CK(launch_setup_graphs((int)n, (int)n_graphs, L.gptr_dev, L.nrem_dev, n_graphs > 1 ? L.gid_dev : nullptr, L.teff_dev,
                            stream));
     // device-side timing of the two phases (read back with the counts; no extra synchronisation)
@@ -397,6 +392,16 @@ int rlap_schur_eliminate(int64_t n, int64_t nnz, const int32_t* csr_ptr, const i
         for (int i = 0; i < 6; i++) stats[9 + i] = (int64_t)(hstats[ST_T_INIT + i] / 1000);  // phase times, us
         stats[15] = (int64_t)hstats[7];  // debug check: vertices whose scattered count != live counter
         if (hstats[7]) fprintf(stderr, "rlap debug: %llu live/scatter mismatches, last idx %llu scattered %llu live %llu\n", hstats[7], hstats[6] >> 32, (hstats[6] >> 16) & 0xffff, hstats[6] & 0xffff);
+    }
+    if ((flags & 128) && getenv("RLAP_DEBUG_TIMERS")) {   // mean barrier wait per warp and phase, microseconds
+        int blocks = 0;
+        eliminate_grid(&blocks);
+        const double nwarps = (double)blocks * WARPS_PER_BLOCK;
+        static const char* nm[6] = {"init", "A", "B", "C", "D1", "D2"};
+        fprintf(stderr, "rlap timers (us): k_eliminate %.0f |", 0.0 + (double)(stats ? stats[7] : 0));
+        for (int i = 0; i < 6; i++)
+            fprintf(stderr, " %s %.0f (wait %.0f)", nm[i], hstats[ST_T_INIT + i] / 1e3, hstats[ST_W_INIT + i] / 1e3 / nwarps);
+        fprintf(stderr, "\n");
     }
     {
         std::lock_guard<std::mutex> lk(g_layout_mutex);

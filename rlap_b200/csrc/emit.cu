@@ -23,21 +23,15 @@ namespace rlap {
 __device__ __forceinline__ int* rawcnt_of(const SchurParams& P) { return P.blk; }
 __device__ __forceinline__ int* cursor_of(const SchurParams& P) { return P.candround; }
 
-__global__ void k_rowid(int n, long long nnz, const int* ptr, int* rowid) {
-    long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= nnz) return;
-    int lo = 0, hi = n;  // last v with ptr[v] <= p
-    while (hi - lo > 1) {
-        int mid = (lo + hi) >> 1;
-        if (__ldg(ptr + mid) <= p) lo = mid; else hi = mid;
-    }
-    rowid[p] = lo;
-}
+// a failed elimination (pool overflow, scratch overflow) leaves reserved-but-unwritten pool slots and inconsistent
+// counters behind: the emission kernels do nothing then, the caller only reads the status
+__device__ __forceinline__ bool run_failed(const SchurParams& P) { return ldcg_i32(P.ctr + CTR_STATUS) != 0; }
 
 __global__ void k_emit_prep(SchurParams P) {
     const long long VN = (long long)P.V * P.n;
     long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= VN) return;
+    if (run_failed(P)) { rawcnt_of(P)[idx] = 0; cursor_of(P)[idx] = 0; P.outcnt[idx] = 0; return; }
     int c = (P.state[idx] != 2) ? P.live[idx] : 0;
     rawcnt_of(P)[idx] = c;
     cursor_of(P)[idx] = 0;
@@ -50,13 +44,74 @@ __device__ __forceinline__ void scatter_one(const SchurParams& P, size_t vb, int
     else set_status(P, 6);
 }
 
-// blockIdx.y = view; grid-stride over the base entries, then over the view's pool entries
+// Base entries: an 8-lane tile per surviving vertex walks its (neighbour-ascending) CSR segment and writes the
+// entries whose neighbour is alive to the front of the vertex's staging segment, in order and without atomics;
+// rows longer than 64 are then served by the whole warp. cursor[v] = number of entries written.
+__global__ void __launch_bounds__(256) k_emit_base(SchurParams P) {
+    if (run_failed(P)) return;
+    const long long VN = (long long)P.V * P.n;
+    const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31, tl = lane & 7, tile = lane >> 3;
+    const unsigned tlt = (1u << tl) - 1u;
+    for (long long base = gw * 4; base < VN; base += nw * 4) {
+        const long long idx = base + tile;
+        int b = 0, nb = 0;
+        long long off = 0;
+        size_t vb = 0;
+        bool big = false;
+        if (idx < VN && P.state[idx] != 2) {
+            const int v = (int)(idx % P.n);
+            vb = (size_t)(idx - v);
+            b = __ldg(P.ptr + v);
+            nb = __ldg(P.ptr + v + 1) - b;
+            off = P.rawoff[idx];
+            big = nb > 64;
+        }
+        int cnt = 0;
+        const int nbmax = __reduce_max_sync(RLAP_FULL_MASK, big ? 0 : nb);   // the tiles of a warp loop in lock step
+        {
+            for (int p0 = 0; p0 < nbmax; p0 += 8) {
+                const int p = p0 + tl;
+                int u = 0;
+                bool ok = !big && p < nb;
+                if (ok) { u = __ldg(P.col + b + p); ok = P.state[vb + u] != 2; }
+                const unsigned m = (__ballot_sync(RLAP_FULL_MASK, ok) >> (tile * 8)) & 0xffu;
+                if (ok) P.raw[off + cnt + __popc(m & tlt)] = pack_a((uint32_t)u, __ldg(P.w + b + p));
+                cnt += __popc(m);
+            }
+            if (!big && tl == 0 && nb > 0) cursor_of(P)[idx] = cnt;
+        }
+        __syncwarp();
+        unsigned todo = __ballot_sync(RLAP_FULL_MASK, big && tl == 0);
+        while (todo) {
+            const int k = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int kb = __shfl_sync(RLAP_FULL_MASK, b, k), knb = __shfl_sync(RLAP_FULL_MASK, nb, k);
+            const long long koff = __shfl_sync(RLAP_FULL_MASK, off, k);
+            const size_t kvb = (size_t)__shfl_sync(RLAP_FULL_MASK, (unsigned long long)vb, k);
+            int c = 0;
+            for (int p0 = 0; p0 < knb; p0 += 32) {
+                const int p = p0 + lane;
+                int u = 0;
+                bool ok = p < knb;
+                if (ok) { u = __ldg(P.col + kb + p); ok = P.state[kvb + u] != 2; }
+                const unsigned m = __ballot_sync(RLAP_FULL_MASK, ok);
+                if (ok) P.raw[koff + c + __popc(m & ((1u << lane) - 1u))] = pack_a((uint32_t)u, __ldg(P.w + kb + p));
+                c += __popc(m);
+            }
+            if (lane == 0) cursor_of(P)[base + (k >> 3)] = c;
+        }
+    }
+}
+
+// Fill entries: grid-stride over the view's pool (blockIdx.y = view); an entry whose two endpoints are alive goes
+// behind the base entries of its owner
 __global__ void __launch_bounds__(256) k_emit_scatter(SchurParams P) {
+    if (run_failed(P)) return;
     const int view = blockIdx.y;
     const size_t vb = (size_t)view * (size_t)P.n;
     const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x, nt = (long long)gridDim.x * blockDim.x;
-    for (long long p = t0; p < P.nnz; p += nt)
-        scatter_one(P, vb, __ldg(P.rowid + p), __ldg(P.col + p), __float_as_uint(__ldg(P.w + p)));
     long long used = (long long)P.pool_cursor[view];
     if (used > P.pool_cap) used = P.pool_cap;
     const int4* pool = P.pool + (size_t)view * (size_t)P.pool_cap;
@@ -233,6 +288,7 @@ __device__ void emit_sort_regs(const SchurParams& P, size_t idx, int lv, long lo
 }
 
 constexpr int CAP_REGS = 512;   // largest segment sorted in registers
+constexpr int CAP_BIG = 12288;   // largest segment sorted in the shared memory of one SM (k_emit_sort_big)
 
 __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_emit_sort_warp(SchurParams P) {
     const long long VN = (long long)P.V * P.n;
@@ -279,7 +335,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_emit_sort_warp(SchurParams
         }
         if (lv > 32 && lv <= CAP_REGS) {
             int pos = atomicAdd(P.ctr + CTR_EMIT_ML, 1);
-            P.wl[pos] = (unsigned int)idx;       // the work list is free once the elimination kernel has returned
+            const unsigned cls = lv <= 64 ? 0u : lv <= 128 ? 1u : lv <= 256 ? 2u : 3u;
+            P.wl[pos] = (unsigned int)idx | (cls << 30);   // the work list is free once the elimination kernel has returned
         }
         if (defer) {   // more than CAP_REGS entries: staged path, one block per segment
             int pos = atomicAdd(P.ctr + CTR_EMIT_DL, 1);
@@ -288,19 +345,35 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_emit_sort_warp(SchurParams
     }
 }
 
-// segments of 33..512 entries: one warp each, registers only
-__global__ void __launch_bounds__(256, 2) k_emit_sort_mid(SchurParams P) {
+// segments of 33..512 entries: one warp each, registers only. One kernel per size class (64, 128, 256, 512 entries =
+// 2, 4, 8, 16 keys per lane) so that the small classes, which hold most segments, run at their own register budget.
+// The list entry carries the class in its two top bits (V * n < 2^30); a warp takes 32 entries, reads their
+// counts and offsets in one go and sorts the ones of its class.
+template <int R>
+__global__ void __launch_bounds__(256, (R <= 4 ? 4 : 2)) k_emit_sort_mid(SchurParams P) {
+    constexpr unsigned CLS = (R == 2 ? 0u : R == 4 ? 1u : R == 8 ? 2u : 3u);
     const int gw = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int nw = (int)(((long long)gridDim.x * blockDim.x) >> 5);
+    const int lane = threadIdx.x & 31;
     const int end = P.ctr[CTR_EMIT_ML];
-    for (int it = gw; it < end; it += nw) {
-        const unsigned int idx = P.wl[it];
-        const int lv = rawcnt_of(P)[idx];
-        const long long off = P.rawoff[idx];
-        if (lv <= 64) emit_sort_regs<2>(P, idx, lv, off);
-        else if (lv <= 128) emit_sort_regs<4>(P, idx, lv, off);
-        else if (lv <= 256) emit_sort_regs<8>(P, idx, lv, off);
-        else emit_sort_regs<16>(P, idx, lv, off);
+    for (int it0 = gw * 32; it0 < end; it0 += nw * 32) {
+        unsigned int idx = 0;
+        int lv = 0;
+        long long off = 0;
+        bool mine = false;
+        if (it0 + lane < end) {
+            const unsigned int e = P.wl[it0 + lane];
+            mine = (e >> 30) == CLS;
+            idx = e & 0x3fffffffu;
+            if (mine) { lv = rawcnt_of(P)[idx]; off = P.rawoff[idx]; }
+        }
+        unsigned todo = __ballot_sync(RLAP_FULL_MASK, mine);
+        while (todo) {
+            const int k = __ffs(todo) - 1;
+            todo &= todo - 1;
+            emit_sort_regs<R>(P, __shfl_sync(RLAP_FULL_MASK, idx, k), __shfl_sync(RLAP_FULL_MASK, lv, k),
+                              __shfl_sync(RLAP_FULL_MASK, off, k));
+        }
     }
 }
 
@@ -317,11 +390,30 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_emit_sort_block(SchurParam
         int j = 0;
         for (int it = 0; it < end; it++) {
             unsigned int idx = P.dl[it];
-            if (rawcnt_of(P)[idx] <= CAP_CTA) continue;
+            if (rawcnt_of(P)[idx] <= CAP_BIG) continue;
             if ((j++ % NSLOT) != (int)blockIdx.x) continue;
             emit_sort_staged<true>(P, idx, scratch_buf(P), &cs);
             __syncthreads();
         }
+    }
+}
+
+// segments of CAP_CTA + 1 .. CAP_BIG entries (the hubs that survive): one block per SM with most of its shared
+// memory as the staging area (keys + fixed-point weights), instead of the global scratch slots
+__global__ void __launch_bounds__(BLOCK_THREADS, 1) k_emit_sort_big(SchurParams P) {
+    extern __shared__ __align__(16) uint64_t smem[];
+    __shared__ CtaScratch cs;
+    StarBuf sb;
+    sb.A = smem; sb.Q = smem + CAP_BIG; sb.K = sb.Q; sb.cap = CAP_BIG;
+    const int end = P.ctr[CTR_EMIT_DL];
+    int j = 0;
+    for (int it = 0; it < end; it++) {
+        unsigned int idx = P.dl[it];
+        const int c = rawcnt_of(P)[idx];
+        if (c <= CAP_CTA || c > CAP_BIG) continue;
+        if ((j++ % (int)gridDim.x) != (int)blockIdx.x) continue;
+        emit_sort_staged<true>(P, idx, sb, &cs);
+        __syncthreads();
     }
 }
 
@@ -367,16 +459,13 @@ __global__ void __launch_bounds__(256) k_emit_copy(SchurParams P, int* out_row, 
 // ---------------------------------------------------------------------------------------------
 cudaError_t eliminate_grid(int* blocks_out);
 
-cudaError_t launch_rowid(int n, long long nnz, const int* ptr, int* rowid, cudaStream_t stream) {
-    if (nnz > 0) k_rowid<<<(unsigned)((nnz + 255) / 256), 256, 0, stream>>>(n, nnz, ptr, rowid);
-    return cudaGetLastError();
-}
-
 cudaError_t launch_emit_count(const SchurParams& P, long long* total_dev, cudaStream_t stream) {
     static bool attr_done = false;
     const size_t smem = (size_t)3 * CAP_CTA * sizeof(uint64_t);
+    const size_t smem_big = (size_t)2 * CAP_BIG * sizeof(uint64_t);
     if (!attr_done) {
         cudaFuncSetAttribute(k_emit_sort_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_emit_sort_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big);
         attr_done = true;
     }
     const long long VN = (long long)P.V * P.n;
@@ -386,8 +475,12 @@ cudaError_t launch_emit_count(const SchurParams& P, long long* total_dev, cudaSt
     e = launch_exclusive_scan<long long>(P.blk, VN, P.rawoff, P.blocksum, nullptr, stream);
     if (e != cudaSuccess) return e;
     {
-        long long work = P.nnz > P.pool_cap ? P.nnz : P.pool_cap;
-        long long bx = (work + 256 * 4 - 1) / (256 * 4);
+        long long bx = (VN / 4 * 32 + 255) / 256;   // one 8-lane tile per vertex
+        if (bx < 1) bx = 1;
+        if (bx > 148 * 16) bx = 148 * 16;
+        k_emit_base<<<(unsigned)bx, 256, 0, stream>>>(P);
+        long long work = P.pool_cap;
+        bx = (work + 256 * 4 - 1) / (256 * 4);
         if (bx < 1) bx = 1;
         if (bx > 148 * 8) bx = 148 * 8;
         k_emit_scatter<<<dim3((unsigned)bx, (unsigned)P.V), 256, 0, stream>>>(P);
@@ -397,8 +490,12 @@ cudaError_t launch_emit_count(const SchurParams& P, long long* total_dev, cudaSt
     e = eliminate_grid(&blocks);
     if (e != cudaSuccess) return e;
     k_emit_sort_warp<<<blocks * 2, BLOCK_THREADS, 0, stream>>>(P);
-    k_emit_sort_mid<<<148 * 8, 256, 0, stream>>>(P);
+    k_emit_sort_mid<2><<<148 * 8, 256, 0, stream>>>(P);
+    k_emit_sort_mid<4><<<148 * 8, 256, 0, stream>>>(P);
+    k_emit_sort_mid<8><<<148 * 4, 256, 0, stream>>>(P);
+    k_emit_sort_mid<16><<<148 * 4, 256, 0, stream>>>(P);
     k_emit_sort_block<<<blocks, BLOCK_THREADS, smem, stream>>>(P);
+    k_emit_sort_big<<<blocks / 2, BLOCK_THREADS, smem_big, stream>>>(P);
     return launch_exclusive_scan<long long>(P.outcnt, VN, P.outoff, P.blocksum, total_dev, stream);
 }
 

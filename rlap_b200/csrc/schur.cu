@@ -135,12 +135,24 @@ __device__ __forceinline__ void push_entry(const SchurParams& P, size_t vb, int4
     if (LIVE) atomicAdd(P.live + vb + owner, 1);
 }
 
+// The two pool entries of a fill edge whose `next` fields are still on their way back from the list-head
+// exchanges. Writing them is deferred until the tile has issued the loads of its next star, so the warp never
+// waits for the exchange round trip (degree / coarsen: a grid barrier separates the writers of a list from its
+// readers; o_v = random flushes before its fence).
+struct PendingPush {
+    int4 e0, e1;
+    int4* p0 = nullptr;
+    __device__ __forceinline__ void flush() {
+        if (p0) { p0[0] = e0; p0[1] = e1; p0 = nullptr; }
+    }
+};
+
 // fill edge (j,k,w): append to both endpoints; o_v = random also records the new dependency.
 // LIVE: bump the live counters of both endpoints here (the register tiles apply net deltas instead).
 // Returns false for an underflowed fill (weight 0: not created).
 template <bool LIVE>
 __device__ __forceinline__ bool push_fill(const SchurParams& P, size_t vb, int4* pool, int j, int k, float w,
-                                          long long slot) {
+                                          long long slot, PendingPush* pend = nullptr) {
     if (!(w > 0.f)) {  // underflowed fill: leave two tombstones so that the pool can be read linearly
         pool[slot] = make_int4(-1, 0, -1, -1);
         pool[slot + 1] = make_int4(-1, 0, -1, -1);
@@ -150,8 +162,14 @@ __device__ __forceinline__ bool push_fill(const SchurParams& P, size_t vb, int4*
         const int s0 = (int)slot, s1 = (int)slot + 1;
         const int n0 = atomicExch(P.head + vb + j, s0);
         const int n1 = atomicExch(P.head + vb + k, s1);
-        pool[s0] = make_int4(k, __float_as_int(w), n0, j);
-        pool[s1] = make_int4(j, __float_as_int(w), n1, k);
+        if (pend) {
+            pend->e0 = make_int4(k, __float_as_int(w), n0, j);
+            pend->e1 = make_int4(j, __float_as_int(w), n1, k);
+            pend->p0 = pool + s0;
+        } else {
+            pool[s0] = make_int4(k, __float_as_int(w), n0, j);
+            pool[s1] = make_int4(j, __float_as_int(w), n1, k);
+        }
         if (LIVE) { atomicAdd(P.live + vb + j, 1); atomicAdd(P.live + vb + k, 1); }
     }
     if (P.o_v == 0) {
@@ -294,13 +312,14 @@ __device__ void eliminate_star(const SchurParams& P, const RoundCtx& rc, int vie
 
 // Register-resident elimination: a tile of W lanes (8, 16 or 32) holds one star, one entry per lane, and
 // the 32 / W tiles of a warp run in lock step (all shuffles are tile-wide). `idx` is the tile's work
-// item (uniform inside the tile) or 0xffffffff for an idle tile. Returns true for the lanes of a tile
-// whose star did not fit (raw list, dead entries included, longer than W): nothing was done for it and
-// the caller retries on a wider tile or the shared-memory path. Same arithmetic, same result.
+// item (uniform inside the tile) or 0xffffffff for an idle tile. The caller has already read the star's CSR
+// bounds (b, nb) and walked its fill list into shared memory (`fills`, nfill entries), and guarantees
+// nb + nfill <= W: the raw list always fits, nothing is retried.
 // `slot0` / `nslots`: pool slots reserved for this star by the caller (an upper bound, 2 per possible fill).
 template <int W>
-__device__ bool eliminate_star_tile(const SchurParams& P, const RoundCtx& rc, unsigned int idx, long long slot0,
-                                    int nslots, LocalStats& ls) {
+__device__ void eliminate_star_tile(const SchurParams& P, const RoundCtx& rc, unsigned int idx, int b, int nb,
+                                    const uint64_t* fills, int nfill, long long slot0, int nslots, LocalStats& ls,
+                                    PendingPush& pend) {
     typedef Tile<W> T;
     const int tl = T::tl();
     const bool active = idx != 0xffffffffu;
@@ -308,27 +327,17 @@ __device__ bool eliminate_star_tile(const SchurParams& P, const RoundCtx& rc, un
     const size_t vb = (size_t)view * (size_t)P.n;
     const uint32_t view_id = P.view_base + (uint32_t)view;
     int4* pool = P.pool + (size_t)view * (size_t)P.pool_cap;
-    bool fail = false;
+    const bool fail = false;
     uint64_t a = RLAP_PAD_A;
     if (active) {
-        const int b = __ldg(P.ptr + v), nb = __ldg(P.ptr + v + 1) - b;
-        if (nb > W) {
-            fail = true;
-        } else {
-            if (tl < nb) a = pack_a((uint32_t)__ldg(P.col + b + tl), __ldg(P.w + b + tl));
-            int slot = nb;
-            int p = ldcg_i32(P.head + vb + v);
-            while (p >= 0 && slot < W) {
-                int4 en = __ldcg(pool + p);
-                if (tl == slot) a = pack_a((uint32_t)en.x, __int_as_float(en.y));
-                slot++;
-                p = en.z;
-            }
-            if (p >= 0) fail = true;
-        }
-        if (fail) a = RLAP_PAD_A;
-        else if (a != RLAP_PAD_A && ldcg_u8(P.state + vb + a_nbr(a)) == 2) a = RLAP_PAD_A;
+        if (tl < nb) a = pack_a((uint32_t)__ldg(P.col + b + tl), __ldg(P.w + b + tl));
+        else if (tl - nb < nfill) a = fills[tl - nb];
     }
+    bool dead = false;
+    if (a != RLAP_PAD_A) dead = ldcg_u8(P.state + vb + a_nbr(a)) == 2;
+    // the previous star's pool entries: their `next` fields have arrived by now
+    pend.flush();
+    if (dead) a = RLAP_PAD_A;
     __syncwarp();
     const bool go = active && !fail;
     a = T::sort_u64(a);
@@ -400,7 +409,7 @@ __device__ bool eliminate_star_tile(const SchurParams& P, const RoundCtx& rc, un
             const double wk = (double)a_w(ek), wm = (double)a_w(a);
             float w = __double2float_rn(__ddiv_rn(__dmul_rn(wk, wm), __dadd_rn(wk, wm)));
             int sl = tl < koff ? tl : tl - 1;
-            done = push_fill<false>(P, vb, pool, (int)a_nbr(a), (int)a_nbr(ek), w, slot0 + 2LL * sl);
+            done = push_fill<false>(P, vb, pool, (int)a_nbr(a), (int)a_nbr(ek), w, slot0 + 2LL * sl, &pend);
         }
         unsigned dm = T::ballot(done);
         if (done) delta++;
@@ -420,7 +429,7 @@ __device__ bool eliminate_star_tile(const SchurParams& P, const RoundCtx& rc, un
         const uint64_t ek = __shfl_sync(RLAP_FULL_MASK, a, koff, W);
         if (emit && act) {
             float w = __double2float_rn(__ddiv_rn(__dmul_rn((double)a_w(a), __ull2double_rn(rem)), __ull2double_rn(S)));
-            if (push_fill<false>(P, vb, pool, (int)a_nbr(a), (int)a_nbr(ek), w, slot0 + 2LL * tl)) {
+            if (push_fill<false>(P, vb, pool, (int)a_nbr(a), (int)a_nbr(ek), w, slot0 + 2LL * tl, &pend)) {
                 delta++;
                 atomicAdd(P.live + vb + (int)a_nbr(ek), 1);
             }
@@ -428,7 +437,7 @@ __device__ bool eliminate_star_tile(const SchurParams& P, const RoundCtx& rc, un
     }
     // o_v = random: pushes and dependency increments are ordered before the decrements;
     // the other orders separate rounds by grid barriers
-    if (P.o_v == 0) __threadfence();
+    if (P.o_v == 0) { pend.flush(); __threadfence(); }
     __syncwarp();
     if (go && tl < L && delta != 0) atomicAdd(P.live + vb + (int)a_nbr(a), delta);
     if (go && rawvalid) {
@@ -447,81 +456,119 @@ __device__ bool eliminate_star_tile(const SchurParams& P, const RoundCtx& rc, un
         P.state[vb + v] = 2;
     }
     __syncwarp();
-    return active && fail;
 }
 
 // ---------------------------------------------------------------------------------------------
 // the persistent elimination kernel
 // ---------------------------------------------------------------------------------------------
 
+constexpr int FCAP = 8;   // fill entries per item that the chunk prologue stages in shared memory
+
 // Run one tier: the items whose bit is set in `mask` (lane i holds item i of the warp's chunk) are handed
-// to the 32 / W tiles of the warp, 32 / W at a time. Returns the mask of items that did not fit.
+// to the 32 / W tiles of the warp, 32 / W at a time.
 template <int W>
-__device__ unsigned run_tier(const SchurParams& P, const RoundCtx& rc, unsigned mask, unsigned int my_idx,
-                             long long my_slot0, int my_nslots, LocalStats& ls) {
+__device__ void run_tier(const SchurParams& P, const RoundCtx& rc, unsigned mask, unsigned int my_idx, int my_b,
+                         int my_nb, int my_nfill, const uint64_t* fbuf, long long my_slot0, int my_nslots,
+                         LocalStats& ls, PendingPush& pend) {
     constexpr int TPW = 32 / W;
     const int lane = threadIdx.x & 31;
     const int tile = lane / W;
-    unsigned failed = 0;
     while (mask) {
         // tile t takes the t-th pending item (lowest set bits first)
         unsigned rest = mask;
         unsigned src = 0xffffffffu;
-        unsigned took[TPW];
 #pragma unroll
         for (int t = 0; t < TPW; t++) {
-            took[t] = rest ? (unsigned)(__ffs(rest) - 1) : 0xffffffffu;
-            if (t == tile) src = took[t];
+            const unsigned took = rest ? (unsigned)(__ffs(rest) - 1) : 0xffffffffu;
+            if (t == tile) src = took;
             rest &= rest - 1;          // 0 & anything stays 0
         }
-        unsigned int idx = __shfl_sync(RLAP_FULL_MASK, my_idx, src & 31);
-        long long sl0 = __shfl_sync(RLAP_FULL_MASK, my_slot0, src & 31);
-        int nsl = __shfl_sync(RLAP_FULL_MASK, my_nslots, src & 31);
+        const int sl = (int)(src & 31);
+        unsigned int idx = __shfl_sync(RLAP_FULL_MASK, my_idx, sl);
+        const int b = __shfl_sync(RLAP_FULL_MASK, my_b, sl), nb = __shfl_sync(RLAP_FULL_MASK, my_nb, sl);
+        const int nfill = __shfl_sync(RLAP_FULL_MASK, my_nfill, sl);
+        const long long sl0 = __shfl_sync(RLAP_FULL_MASK, my_slot0, sl);
+        const int nsl = __shfl_sync(RLAP_FULL_MASK, my_nslots, sl);
         if (src == 0xffffffffu) idx = 0xffffffffu;
-        bool f = eliminate_star_tile<W>(P, rc, idx, sl0, nsl, ls);
-        unsigned fm = __ballot_sync(RLAP_FULL_MASK, f && (lane & (W - 1)) == 0);
-#pragma unroll
-        for (int t = 0; t < TPW; t++)
-            if (took[t] != 0xffffffffu && ((fm >> (t * W)) & 1u)) failed |= 1u << took[t];
+        eliminate_star_tile<W>(P, rc, idx, b, nb, fbuf + sl * FCAP, nfill, sl0, nsl, ls, pend);
         mask = rest;
     }
-    return failed;
 }
 
 // process work-list items [start, end): a warp takes a chunk of up to 32 items and serves them tier by
 // tier (8-, 16-, 32-lane register tiles, then the shared-memory path); big stars go to the block phase
-__device__ void run_warp_items(const SchurParams& P, const RoundCtx& rc, uint64_t* smem, CtaScratch* cs, int start,
-                               int end, LocalStats& ls) {
+__device__ void run_warp_items(const SchurParams& P, const RoundCtx& rc, uint64_t* smem, CtaScratch* cs, int* next,
+                               int start, int end, LocalStats& ls) {
     const int gw = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int nw = (int)((gridDim.x * blockDim.x) >> 5);
     const int lane = threadIdx.x & 31;
     StarBuf sb = warp_buf(smem);
+    uint64_t* fbuf = sb.A;   // 32 x FCAP staged fill entries; the shared-memory path reuses the area afterwards
     const int count = end - start;
     if (count <= 0) return;
-    int chunk = (count + nw - 1) / nw;       // spread small rounds over all warps
-    if (chunk > 32) chunk = 32;
-    for (int c0 = start + gw * chunk; c0 < end; c0 += nw * chunk) {
+    // Every block owns a contiguous slice of the items; its warps fetch chunks of the slice from a shared-memory
+    // cursor, so a warp that drew expensive stars takes fewer chunks (a static stride left the phase waiting for the
+    // warps with one chunk more than the others). flags & 256: the static schedule, for comparison.
+    const bool dynamic = (P.flags & 256) == 0;
+    int chunk, c0, cstep, my_end;
+    if (dynamic) {
+        const long long nb = gridDim.x, bid = blockIdx.x;
+        const int bs = start + (int)((long long)count * bid / nb), be = start + (int)((long long)count * (bid + 1) / nb);
+        chunk = (be - bs + 3 * WARPS_PER_BLOCK - 1) / (3 * WARPS_PER_BLOCK);
+        chunk = (chunk + 3) & ~3;
+        if (chunk > 32) chunk = 32;
+        if (chunk < 4) chunk = 4;
+        if (threadIdx.x == 0) *next = bs;
+        __syncthreads();
+        my_end = be;
+        c0 = 0; cstep = 0;
+    } else {
+        chunk = (count + nw - 1) / nw;       // spread small rounds over all warps
+        if (chunk > 32) chunk = 32;
+        c0 = start + gw * chunk; cstep = nw * chunk; my_end = end;
+    }
+    for (;; c0 += cstep) {
+        if (dynamic) {
+            if (lane == 0) c0 = atomicAdd(next, chunk);
+            c0 = __shfl_sync(RLAP_FULL_MASK, c0, 0);
+        }
+        if (c0 >= my_end) break;
+        const int end = my_end;
         const int it = c0 + lane;
         unsigned int idx = 0xffffffffu;
-        int lv = -1, cls = -1;
+        int lv = -1, cls = -1, b = 0, nb = 0, nfill = 0;
+        __syncwarp();   // the previous chunk is done with the staging buffer
         if (lane < chunk && it < end) {
             idx = __ldcg(P.wl + it);
+            const int view = (int)(idx / (unsigned)P.n), v = (int)(idx % (unsigned)P.n);
             bool skip = false;
             if (P.o_v != 0) {  // truncated final round of a graph: only the highest ids go
-                int view = (int)(idx / (unsigned)P.n), v = (int)(idx % (unsigned)P.n);
                 size_t seg = (size_t)view * P.G + graph_of(P, v);
                 skip = ldcg_i32(P.ovfseg + seg) && idx < __ldcg(P.thresh + seg);
             }
             if (!skip) {
                 lv = ldcg_i32(P.live + idx);
-                // the register tiles hold the whole raw list: the base segment bounds it from below
-                int v = (int)(idx % (unsigned)P.n);
-                int nb = __ldg(P.ptr + v + 1) - __ldg(P.ptr + v);
-                if (lv <= CAP_WARP) cls = max(lv, nb);
-                else cls = lv;
-                if ((P.flags & 64) && lv <= CAP_WARP) cls = 33;   // debug: no register tiles
+                b = __ldg(P.ptr + v);
+                nb = __ldg(P.ptr + v + 1) - b;
+                if (lv <= CAP_WARP) {
+                    // every lane walks the fill list of its own item (32 chains in flight) into the staging buffer;
+                    // with the CSR bounds this gives the exact raw length, i.e. the tile width that holds the star
+                    const int4* pool = P.pool + (size_t)view * (size_t)P.pool_cap;
+                    int p = ldcg_i32(P.head + idx);
+                    while (p >= 0 && nfill < FCAP) {
+                        const int4 en = __ldcg(pool + p);
+                        fbuf[lane * FCAP + nfill] = pack_a((uint32_t)en.x, __int_as_float(en.y));
+                        nfill++;
+                        p = en.z;
+                    }
+                    cls = (p >= 0 || nb + nfill > 32) ? 33 : nb + nfill;   // 33: the shared-memory path gathers it itself
+                    if (P.flags & 64) cls = 33;   // debug: no register tiles
+                } else {
+                    cls = lv;
+                }
             }
         }
+        __syncwarp();
         if (lv > CAP_WARP) {
             int pos = rc.dl_base + atomicAdd(P.ctr + rc.dslot, 1);
             P.dl[pos] = idx;
@@ -560,17 +607,12 @@ __device__ void run_warp_items(const SchurParams& P, const RoundCtx& rc, uint64_
                 }
             }
         }
-        m16 |= run_tier<8>(P, rc, m8, idx, slot0, nslots, ls);
-        m32 |= run_tier<16>(P, rc, m16, idx, slot0, nslots, ls);
-        msm |= run_tier<32>(P, rc, m32, idx, slot0, nslots, ls);
-        // stars that fell through every register tier keep their reservation unused: tombstone it
-        {
-            unsigned fell = msm & __ballot_sync(RLAP_FULL_MASK, nslots > 0);
-            if (((fell >> lane) & 1u) && slot0 + nslots <= P.pool_cap) {
-                int4* pool = P.pool + (size_t)(idx / (unsigned)P.n) * (size_t)P.pool_cap;
-                for (int u = 0; u < nslots; u++) pool[slot0 + u] = make_int4(-1, 0, -1, -1);
-            }
-        }
+        PendingPush pend;
+        run_tier<8>(P, rc, m8, idx, b, nb, nfill, fbuf, slot0, nslots, ls, pend);
+        run_tier<16>(P, rc, m16, idx, b, nb, nfill, fbuf, slot0, nslots, ls, pend);
+        run_tier<32>(P, rc, m32, idx, b, nb, nfill, fbuf, slot0, nslots, ls, pend);
+        pend.flush();
+        __syncwarp();
         while (msm) {
             int k = __ffs(msm) - 1;
             msm &= msm - 1;
@@ -606,6 +648,7 @@ __device__ void run_block_items(const SchurParams& P, const RoundCtx& rc, uint64
 __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
     extern __shared__ __align__(16) uint64_t smem[];
     __shared__ CtaScratch cs;
+    __shared__ int s_next;
     cg::grid_group grid = cg::this_grid();
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long nthr = (long long)gridDim.x * blockDim.x;
@@ -656,6 +699,19 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
         }
     };
     lap(-1);
+    // grid barrier that ends a phase; with flags & 128 every warp also records how long it waited there
+    const bool wait_timers = (P.flags & 128) != 0;
+    auto gsync = [&](int slot) {
+        unsigned long long t0 = 0;
+        if (wait_timers && (threadIdx.x & 31) == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        grid.sync();
+        if (wait_timers && (threadIdx.x & 31) == 0) {
+            unsigned long long t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            atomicAdd(P.stats + ST_W_INIT + (slot - ST_T_INIT), t1 - t0);
+        }
+        lap(slot);
+    };
     int wl_start = 0;   // first unconsumed work-list item
     int dl_start = 0;
     int rounds = 0;
@@ -711,8 +767,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
                 if (root) P.wl[pos0 + __popc(rm & lt)] = idx;
             }
         }
-        grid.sync();
-        lap(ST_T_INIT);
+        gsync(ST_T_INIT);
         while (true) {
             // items to consume were appended in the previous round
             int wl_end = wl_start + ldcg_i32(P.ctr + CTR_WCNT0 + (rounds + 2) % 3);
@@ -720,16 +775,14 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
             if (tid == 0) { P.ctr[CTR_WCNT0 + (rounds + 1) % 3] = 0; P.ctr[CTR_DCNT0 + (rounds + 1) % 3] = 0; }
             rc.wl_base = wl_end; rc.wslot = CTR_WCNT0 + rounds % 3;
             rc.dl_base = dl_start; rc.dslot = CTR_DCNT0 + rounds % 3;
-            run_warp_items(P, rc, smem, &cs, wl_start, wl_end, ls);
+            run_warp_items(P, rc, smem, &cs, &s_next, wl_start, wl_end, ls);
             wl_start = wl_end;
-            grid.sync();
-            lap(ST_T_D1);
+            gsync(ST_T_D1);
             int dl_end = dl_start + ldcg_i32(P.ctr + rc.dslot);
             if (dl_end != dl_start) {
                 run_block_items(P, rc, smem, &cs, dl_start, dl_end, ls);
                 dl_start = dl_end;
-                grid.sync();
-                lap(ST_T_D2);
+                gsync(ST_T_D2);
             }
             rounds++;
         }
@@ -811,8 +864,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
                 }
                 if (any && lane == 0) P.ctr[CTR_ACTIVE0 + par] = 1;
             }
-            grid.sync();
-            lap(ST_T_A);
+            gsync(ST_T_A);
             if (ldcg_i32(P.ctr + CTR_ACTIVE0 + par) == 0) break;
             // phase B: members of the minimum bucket with no bucket neighbour of higher id
             // shared memory during this phase (the star buffers are idle): per-segment rem / min-key copies and
@@ -928,8 +980,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
                 }
             }
             __syncthreads();   // the shared copies are star buffers again from here on
-            grid.sync();
-            lap(ST_T_B);
+            gsync(ST_T_B);
             // phase C: a graph that selected more than it may still remove keeps its highest ids
             if (ldcg_i32(P.ctr + CTR_OVF0 + par)) {
                 const int gw = (int)(tid >> 5), nw = (int)(nthr >> 5), lane = threadIdx.x & 31;
@@ -998,8 +1049,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
                     }
                     if (lane == 0) { P.thresh[s] = (unsigned int)T; P.ovfseg[s] = 1; }
                 }
-                grid.sync();
-                lap(ST_T_C);
+                gsync(ST_T_C);
             }
             // the truncated count is what phase D will eliminate
             for (long long q = tid; q < VG; q += nthr) {
@@ -1008,16 +1058,14 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
             }
             // phase D: eliminate
             int wl_end = wl_start + ldcg_i32(P.ctr + rc.wslot);
-            run_warp_items(P, rc, smem, &cs, wl_start, wl_end, ls);
+            run_warp_items(P, rc, smem, &cs, &s_next, wl_start, wl_end, ls);
             wl_start = wl_end;
-            grid.sync();
-            lap(ST_T_D1);
+            gsync(ST_T_D1);
             int dl_end = dl_start + ldcg_i32(P.ctr + rc.dslot);
             if (dl_end != dl_start) {
                 run_block_items(P, rc, smem, &cs, dl_start, dl_end, ls);
                 dl_start = dl_end;
-                grid.sync();
-                lap(ST_T_D2);
+                gsync(ST_T_D2);
             }
             rounds++;
         }

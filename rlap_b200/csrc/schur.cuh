@@ -41,7 +41,9 @@ struct RoundCtx {
     int dslot;
 };
 enum { ST_FILLS = 0, ST_POOL_MAX = 1, ST_MAXSTAR = 2, ST_DEFERRED = 3, ST_RAW = 4,
-       ST_T_INIT = 8, ST_T_A = 9, ST_T_B = 10, ST_T_C = 11, ST_T_D1 = 12, ST_T_D2 = 13, ST_COUNT = 16 };
+       ST_T_INIT = 8, ST_T_A = 9, ST_T_B = 10, ST_T_C = 11, ST_T_D1 = 12, ST_T_D2 = 13,
+       ST_W_INIT = 16 /* .. 21: warp-nanoseconds spent waiting at the grid barrier that ends each phase (flags & 128) */,
+       ST_COUNT = 24 };
 
 struct SchurParams {
     // coalesced graph (shared by all views, immutable)
@@ -69,7 +71,6 @@ struct SchurParams {
     int* outcnt;       // emission: merged row count
     long long* outoff; // emission: [V*n + 1] exclusive prefix of outcnt
     // emission staging: the live entries of every surviving vertex, owner-major, contiguous
-    const int* rowid;  // [nnz] owner of a CSR entry (graph level)
     long long* rawoff; // [V*n + 1] exclusive prefix of the live counts of surviving vertices
     uint64_t* raw;     // [raw_cap] (nbr << 32) | weight bits
     long long raw_cap;
