@@ -41,7 +41,8 @@ typedef enum {
     RLAP_ERR_STAR_TOO_LARGE = 6,  /* a vertex star exceeded the scratch capacity (scratch_cap)      */
     RLAP_ERR_WORKSPACE = 7,       /* workspace smaller than the *_workspace_bytes answer            */
     RLAP_ERR_CUDA = 8,            /* CUDA runtime error (see rlap_last_cuda_error)                  */
-    RLAP_ERR_NEGATIVE_WEIGHT = 9  /* weight < 0 or not finite                                       */
+    RLAP_ERR_NEGATIVE_WEIGHT = 9, /* weight < 0 or not finite                                       */
+    RLAP_ERR_INTERNAL = 10        /* an internal invariant failed (round bound exceeded): a bug     */
 } rlap_status;
 
 /* o_v: vertex elimination order (factorizers.cc:56-64). o_n: neighbour order (prec.cc:295-307). */

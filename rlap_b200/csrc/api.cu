@@ -110,6 +110,7 @@ const char* rlap_status_string(int s) {
         case RLAP_ERR_WORKSPACE: return "workspace too small";
         case RLAP_ERR_CUDA: return "CUDA error";
         case RLAP_ERR_NEGATIVE_WEIGHT: return "negative or non-finite edge weight";
+        case RLAP_ERR_INTERNAL: return "internal invariant failed (elimination round bound exceeded)";
         default: return "unknown status";
     }
 }
@@ -262,6 +263,7 @@ static SchurLayout schur_layout(long long n, long long nnz, long long G, long lo
     P.pool_cap = pool_cap;
     P.pool_cursor = c.take<unsigned long long>((size_t)V);
     P.rem = c.take<int>(VG);
+    P.lvl = c.take<int>(VG);
     P.minkey = c.take<int>(2 * VG);
     P.cntI = c.take<int>(VG);
     P.ovfseg = c.take<int>(VG);
@@ -269,6 +271,8 @@ static SchurLayout schur_layout(long long n, long long nnz, long long G, long lo
     P.blockcnt = c.take<int>((VN + SEL_BLOCK - 1) / SEL_BLOCK + 1);
     P.wl = c.take<unsigned int>(2 * VN + 1);
     P.dl = c.take<unsigned int>(VN + 1);
+    P.low_cap = (long long)(2 * VN + 64);
+    P.low = c.take<unsigned int>(2 * (size_t)P.low_cap);
     P.scratch = c.take<uint64_t>((size_t)NSLOT * 3 * (size_t)scratch_cap);
     P.scratch_cap = (int)scratch_cap;
     P.blocksum = c.take<long long>((size_t)scan_blocks((long long)VN));

@@ -287,6 +287,19 @@ __device__ void emit_sort_regs(const SchurParams& P, size_t idx, int lv, long lo
     if (lane == 0) P.outcnt[idx] = rowbase;
 }
 
+// Segments of more than 32 entries are listed by size class in dense lists (the low-list buffers of the elimination
+// are free by now): a hub-heavy stretch of vertex ids (the old vertices of a preferential-attachment graph) would
+// otherwise hand all its big segments to the few warps that own that stretch.
+constexpr int N_CLASS = 6;      // 0..3: 64 / 128 / 256 / 512 entries (register sort), 4: <= CAP_CTA, 5: above
+__device__ __forceinline__ unsigned int* class_list(const SchurParams& P, int c) {
+    const size_t VN = (size_t)P.V * (size_t)P.n;
+    if (c == 0) return P.wl;
+    if (c == 1) return P.wl + VN;
+    if (c == 5) return P.dl;
+    return P.low + (size_t)(c - 2) * (VN + 16);
+}
+__device__ __forceinline__ int* class_tail(const SchurParams& P, int c) { return P.ctr + CTR_EMIT_C0 + c; }
+
 constexpr int CAP_REGS = 512;   // largest segment sorted in registers
 constexpr int CAP_BIG = 12288;   // largest segment sorted in the shared memory of one SM (k_emit_sort_big)
 
@@ -305,7 +318,6 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_emit_sort_warp(SchurParams
             off = P.rawoff[idx];
             if (lv == 0) P.outcnt[idx] = 0;
         }
-        bool defer = lv > CAP_REGS;
         // register path: one vertex at a time, all 32 lanes on its (contiguous) segment
         unsigned small = __ballot_sync(RLAP_FULL_MASK, lv > 0 && lv <= 32);
         uint64_t a_next = RLAP_PAD_A;
@@ -333,14 +345,18 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_emit_sort_warp(SchurParams
             if ((hmask >> lane) & 1u) P.raw[koff + __popc(hmask & lt)] = a;
             if (lane == 0) P.outcnt[base + k] = __popc(hmask);
         }
-        if (lv > 32 && lv <= CAP_REGS) {
-            int pos = atomicAdd(P.ctr + CTR_EMIT_ML, 1);
-            const unsigned cls = lv <= 64 ? 0u : lv <= 128 ? 1u : lv <= 256 ? 2u : 3u;
-            P.wl[pos] = (unsigned int)idx | (cls << 30);   // the work list is free once the elimination kernel has returned
-        }
-        if (defer) {   // more than CAP_REGS entries: staged path, one block per segment
-            int pos = atomicAdd(P.ctr + CTR_EMIT_DL, 1);
-            P.dl[pos] = (unsigned int)idx;
+        // bigger segments: dense per-class lists, one tail bump per class and warp pass
+        const int cls = lv <= 32 ? -1 : lv <= 64 ? 0 : lv <= 128 ? 1 : lv <= 256 ? 2 : lv <= CAP_REGS ? 3 : lv <= CAP_CTA ? 4 : 5;
+        if (__any_sync(RLAP_FULL_MASK, cls >= 0)) {
+#pragma unroll
+            for (int c = 0; c < N_CLASS; c++) {
+                const unsigned m = __ballot_sync(RLAP_FULL_MASK, cls == c);
+                if (m == 0) continue;
+                int pos0 = 0;
+                if (lane == __ffs(m) - 1) pos0 = atomicAdd(class_tail(P, c), __popc(m));
+                pos0 = __shfl_sync(RLAP_FULL_MASK, pos0, __ffs(m) - 1);
+                if (cls == c) class_list(P, c)[pos0 + __popc(m & lt)] = (unsigned int)idx;
+            }
         }
     }
 }
@@ -351,47 +367,33 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_emit_sort_warp(SchurParams
 // counts and offsets in one go and sorts the ones of its class.
 template <int R>
 __global__ void __launch_bounds__(256, (R <= 4 ? 4 : 2)) k_emit_sort_mid(SchurParams P) {
-    constexpr unsigned CLS = (R == 2 ? 0u : R == 4 ? 1u : R == 8 ? 2u : 3u);
+    constexpr int CLS = (R == 2 ? 0 : R == 4 ? 1 : R == 8 ? 2 : 3);
     const int gw = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int nw = (int)(((long long)gridDim.x * blockDim.x) >> 5);
-    const int lane = threadIdx.x & 31;
-    const int end = P.ctr[CTR_EMIT_ML];
-    for (int it0 = gw * 32; it0 < end; it0 += nw * 32) {
-        unsigned int idx = 0;
-        int lv = 0;
-        long long off = 0;
-        bool mine = false;
-        if (it0 + lane < end) {
-            const unsigned int e = P.wl[it0 + lane];
-            mine = (e >> 30) == CLS;
-            idx = e & 0x3fffffffu;
-            if (mine) { lv = rawcnt_of(P)[idx]; off = P.rawoff[idx]; }
-        }
-        unsigned todo = __ballot_sync(RLAP_FULL_MASK, mine);
-        while (todo) {
-            const int k = __ffs(todo) - 1;
-            todo &= todo - 1;
-            emit_sort_regs<R>(P, __shfl_sync(RLAP_FULL_MASK, idx, k), __shfl_sync(RLAP_FULL_MASK, lv, k),
-                              __shfl_sync(RLAP_FULL_MASK, off, k));
-        }
+    const int end = *class_tail(P, CLS);
+    const unsigned int* list = class_list(P, CLS);
+    for (int it = gw; it < end; it += nw) {
+        const unsigned int idx = list[it];
+        emit_sort_regs<R>(P, idx, rawcnt_of(P)[idx], P.rawoff[idx]);
     }
 }
 
 __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_emit_sort_block(SchurParams P) {
     extern __shared__ __align__(16) uint64_t smem[];
     __shared__ CtaScratch cs;
-    const int end = P.ctr[CTR_EMIT_DL];
+    const int end = *class_tail(P, 4);
+    const unsigned int* list = class_list(P, 4);
     for (int it = (int)blockIdx.x; it < end; it += (int)gridDim.x) {
-        unsigned int idx = P.dl[it];
-        if (rawcnt_of(P)[idx] <= CAP_CTA) emit_sort_staged<true>(P, idx, cta_buf(smem), &cs);
+        emit_sort_staged<true>(P, list[it], cta_buf(smem), &cs);
         __syncthreads();
     }
+    // segments beyond the shared memory of an SM: the NSLOT blocks that own a global scratch slot
     if ((int)blockIdx.x < NSLOT) {
-        int j = 0;
-        for (int it = 0; it < end; it++) {
-            unsigned int idx = P.dl[it];
+        const int end5 = *class_tail(P, 5);
+        const unsigned int* list5 = class_list(P, 5);
+        for (int it = (int)blockIdx.x; it < end5; it += NSLOT) {
+            const unsigned int idx = list5[it];
             if (rawcnt_of(P)[idx] <= CAP_BIG) continue;
-            if ((j++ % NSLOT) != (int)blockIdx.x) continue;
             emit_sort_staged<true>(P, idx, scratch_buf(P), &cs);
             __syncthreads();
         }
@@ -405,19 +407,19 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 1) k_emit_sort_big(SchurParams 
     __shared__ CtaScratch cs;
     StarBuf sb;
     sb.A = smem; sb.Q = smem + CAP_BIG; sb.K = sb.Q; sb.cap = CAP_BIG;
-    const int end = P.ctr[CTR_EMIT_DL];
-    int j = 0;
-    for (int it = 0; it < end; it++) {
-        unsigned int idx = P.dl[it];
-        const int c = rawcnt_of(P)[idx];
-        if (c <= CAP_CTA || c > CAP_BIG) continue;
-        if ((j++ % (int)gridDim.x) != (int)blockIdx.x) continue;
+    const int end = *class_tail(P, 5);
+    const unsigned int* list = class_list(P, 5);
+    for (int it = (int)blockIdx.x; it < end; it += (int)gridDim.x) {
+        const unsigned int idx = list[it];
+        if (rawcnt_of(P)[idx] > CAP_BIG) continue;
         emit_sort_staged<true>(P, idx, sb, &cs);
         __syncthreads();
     }
 }
 
-// compact copy: merged segment of every survivor -> final rows
+// compact copy: merged segment of every survivor -> final rows. A warp owns 32 consecutive vertices; their rows are
+// contiguous in the output (outoff is the exclusive prefix of outcnt), so the warp walks that output range with all
+// lanes busy and finds the source vertex of every row by a 5-step search over the 32 start offsets.
 __global__ void __launch_bounds__(256) k_emit_copy(SchurParams P, int* out_row, int* out_col, float* out_w,
                                                   double* out_f64) {
     const long long VN = (long long)P.V * P.n;
@@ -426,28 +428,40 @@ __global__ void __launch_bounds__(256) k_emit_copy(SchurParams P, int* out_row, 
     const int lane = threadIdx.x & 31;
     for (long long base = gw * 32; base < VN; base += nw * 32) {
         const long long idx = base + lane;
-        int L = 0;
         long long src = 0, dst = 0;
+        int L = 0;
         if (idx < VN) {
             L = P.outcnt[idx];
             src = P.rawoff[idx];
             dst = P.outoff[idx];
         }
-        unsigned todo = __ballot_sync(RLAP_FULL_MASK, L > 0);
-        while (todo) {
-            const int k = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const int kL = __shfl_sync(RLAP_FULL_MASK, L, k);
-            const long long ksrc = __shfl_sync(RLAP_FULL_MASK, src, k), kdst = __shfl_sync(RLAP_FULL_MASK, dst, k);
-            const int v = (int)((base + k) % P.n);
-            for (int i = lane; i < kL; i += 32) {
-                uint64_t a = P.raw[ksrc + i];
-                long long o = kdst + i;
-                if (out_row) { out_row[o] = (int)a_nbr(a); out_col[o] = v; out_w[o] = a_w(a); }
+        const long long dst0 = __shfl_sync(RLAP_FULL_MASK, dst, 0);
+        // start of lane i's rows relative to the warp's output range; lanes past VN inherit the end of the range
+        int rel = (int)(dst - dst0);
+        const int total = __shfl_sync(RLAP_FULL_MASK, rel + L, 31 < (VN - base - 1) ? 31 : (int)(VN - base - 1));
+        if (idx >= VN) rel = total;
+        const int v0 = (int)(base % P.n);
+        for (int o0 = 0; o0 < total; o0 += 32) {
+            const int o = o0 + lane;
+            // last lane i with rel_i <= o (rows of empty vertices are skipped: equal offsets resolve to the last one)
+            int lo = 0;
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1) {
+                const int r = __shfl_sync(RLAP_FULL_MASK, rel, (lo + step) & 31);
+                if (lo + step < 32 && r <= o) lo += step;
+            }
+            const long long ksrc = __shfl_sync(RLAP_FULL_MASK, src, lo);
+            const int krel = __shfl_sync(RLAP_FULL_MASK, rel, lo);
+            if (o < total) {
+                const uint64_t a = P.raw[ksrc + (o - krel)];
+                int v = v0 + lo;
+                while (v >= P.n) v -= P.n;   // the 32 vertices may straddle view boundaries (tiny graphs: several)
+                const long long w = dst0 + o;
+                if (out_row) { out_row[w] = (int)a_nbr(a); out_col[w] = v; out_w[w] = a_w(a); }
                 if (out_f64) {
-                    out_f64[o * 3 + 0] = (double)a_nbr(a);
-                    out_f64[o * 3 + 1] = (double)v;
-                    out_f64[o * 3 + 2] = (double)a_w(a);
+                    out_f64[w * 3 + 0] = (double)a_nbr(a);
+                    out_f64[w * 3 + 1] = (double)v;
+                    out_f64[w * 3 + 2] = (double)a_w(a);
                 }
             }
         }
@@ -469,7 +483,7 @@ cudaError_t launch_emit_count(const SchurParams& P, long long* total_dev, cudaSt
         attr_done = true;
     }
     const long long VN = (long long)P.V * P.n;
-    cudaError_t e = cudaMemsetAsync(P.ctr + CTR_EMIT_DL, 0, 2 * sizeof(int), stream);
+    cudaError_t e = cudaMemsetAsync(P.ctr + CTR_EMIT_C0, 0, N_CLASS * sizeof(int), stream);
     if (e != cudaSuccess) return e;
     k_emit_prep<<<(unsigned)((VN + 255) / 256), 256, 0, stream>>>(P);
     e = launch_exclusive_scan<long long>(P.blk, VN, P.rawoff, P.blocksum, nullptr, stream);

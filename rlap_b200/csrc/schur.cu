@@ -13,6 +13,7 @@
 // The sequential specification this file implements bit for bit is oracle/rlap_oracle.cc (keyed mode)
 // and DESIGN.md §3.
 #include <cooperative_groups.h>
+#include <stdio.h>
 #include "rlap_device.cuh"
 #include "schur.cuh"
 #include "scan.cuh"
@@ -147,6 +148,39 @@ struct PendingPush {
     }
 };
 
+// degree / coarsen: appends to the next round's low list through a small per-warp shared buffer, so that the list
+// tail is bumped once per few dozen entries. Every member is warp-collective.
+constexpr int LOWBUF = 64;
+struct LowAppender {
+    unsigned int* buf = nullptr;   // [LOWBUF] shared memory, one per warp
+    unsigned int* dst = nullptr;   // nullptr: disabled (o_v = random)
+    long long cap = 0;
+    int* tail = nullptr;
+    int* ovf = nullptr;
+    int fill = 0;
+    __device__ __forceinline__ void flush() {
+        if (fill == 0) return;
+        const int lane = threadIdx.x & 31;
+        int pos0 = 0;
+        if (lane == 0) pos0 = atomicAdd(tail, fill);
+        pos0 = __shfl_sync(RLAP_FULL_MASK, pos0, 0);
+        __syncwarp();
+        for (int i = lane; i < fill; i += 32) {
+            if ((long long)pos0 + i < cap) dst[pos0 + i] = buf[i]; else *ovf = 1;
+        }
+        __syncwarp();
+        fill = 0;
+    }
+    __device__ __forceinline__ void push(bool pred, unsigned int val) {
+        if (dst == nullptr) return;
+        const unsigned m = __ballot_sync(RLAP_FULL_MASK, pred);
+        if (m == 0) return;
+        if (fill + 32 > LOWBUF) flush();
+        if (pred) buf[fill + __popc(m & ((1u << (threadIdx.x & 31)) - 1u))] = val;
+        fill += __popc(m);
+    }
+};
+
 // fill edge (j,k,w): append to both endpoints; o_v = random also records the new dependency.
 // LIVE: bump the live counters of both endpoints here (the register tiles apply net deltas instead).
 // Returns false for an underflowed fill (weight 0: not created).
@@ -186,7 +220,7 @@ struct LocalStats { unsigned long long fills = 0, raw = 0; int maxstar = 0; };
 
 template <bool CTA>
 __device__ void eliminate_star(const SchurParams& P, const RoundCtx& rc, int view, int v, StarBuf sb, CtaScratch* cs,
-                               LocalStats& ls) {
+                               LocalStats& ls, LowAppender& la) {
     const size_t vb = (size_t)view * (size_t)P.n;
     const int gs = g_size<CTA>(), r = g_rank<CTA>();
     const uint32_t view_id = P.view_base + (uint32_t)view;
@@ -287,18 +321,29 @@ __device__ void eliminate_star(const SchurParams& P, const RoundCtx& rc, int vie
         // eventual neighbours are gone
         if (P.o_v == 0) __threadfence();
         g_sync<CTA>();
-        for (int i = r; i < P2; i += gs) {
-            uint64_t a = sb.A[i];
-            if (a == RLAP_PAD_A) continue;
-            int u = (int)a_nbr(a);
-            atomicSub(P.live + vb + u, 1);
-            if (P.o_v == 0 && ldcg_u8(P.state + vb + u) == 1) {
-                int old = atomicSub(P.blk + vb + u, 1);
-                if (old == 1) {
-                    int pos = rc.wl_base + atomicAdd(P.ctr + rc.wslot, 1);
-                    P.wl[pos] = (unsigned int)(vb + (size_t)u);
+        // a neighbour whose live counter moves from above the segment's level to the level or below joins the
+        // next round's low list (degree / coarsen)
+        const int M = (P.o_v != 0) ? ldcg_i32(P.lvl + (size_t)view * P.G + graph_of(P, v)) : -1;
+        for (int base = 0; base < P2; base += gs) {
+            const int i = base + r;
+            bool cross = false;
+            int u = 0;
+            if (i < P2) {
+                const uint64_t a = sb.A[i];
+                if (a != RLAP_PAD_A) {
+                    u = (int)a_nbr(a);
+                    const int old = atomicSub(P.live + vb + u, 1);
+                    cross = old > M && old - 1 <= M;
+                    if (P.o_v == 0 && ldcg_u8(P.state + vb + u) == 1) {
+                        int oldb = atomicSub(P.blk + vb + u, 1);
+                        if (oldb == 1) {
+                            int pos = rc.wl_base + atomicAdd(P.ctr + rc.wslot, 1);
+                            P.wl[pos] = (unsigned int)(vb + (size_t)u);
+                        }
+                    }
                 }
             }
+            la.push(cross, (unsigned int)(vb + (size_t)u));
         }
         if (r == 0) {
             ls.fills += (unsigned long long)(ovf ? 0 : nf);
@@ -318,8 +363,8 @@ __device__ void eliminate_star(const SchurParams& P, const RoundCtx& rc, int vie
 // `slot0` / `nslots`: pool slots reserved for this star by the caller (an upper bound, 2 per possible fill).
 template <int W>
 __device__ void eliminate_star_tile(const SchurParams& P, const RoundCtx& rc, unsigned int idx, int b, int nb,
-                                    const uint64_t* fills, int nfill, long long slot0, int nslots, LocalStats& ls,
-                                    PendingPush& pend) {
+                                    const uint64_t* fills, int nfill, long long slot0, int nslots, int M,
+                                    LocalStats& ls, PendingPush& pend, LowAppender& la) {
     typedef Tile<W> T;
     const int tl = T::tl();
     const bool active = idx != 0xffffffffu;
@@ -351,7 +396,11 @@ __device__ void eliminate_star_tile(const SchurParams& P, const RoundCtx& rc, un
     const int L = __popc(hmask);
     // live counters: a neighbour loses its entries to v (all `mult` of them) and gains one entry per fill it
     // receives. The extra multiplicity goes now, the rest is netted per merged neighbour after sampling.
-    if (go && ((hmask >> tl) & 1u) && mult > 1) atomicSub(P.live + vb + rawnbr, mult - 1);
+    bool cross0 = false;
+    if (go && ((hmask >> tl) & 1u) && mult > 1) {
+        const int old = atomicSub(P.live + vb + rawnbr, mult - 1);
+        cross0 = old > M && old - (mult - 1) <= M;
+    }
     const bool live = (hmask >> tl) & 1u;
     const bool full = (P.flags & 1) != 0;
     const bool coarsen = (P.o_v == 2) && !full;
@@ -439,7 +488,14 @@ __device__ void eliminate_star_tile(const SchurParams& P, const RoundCtx& rc, un
     // the other orders separate rounds by grid barriers
     if (P.o_v == 0) { pend.flush(); __threadfence(); }
     __syncwarp();
-    if (go && tl < L && delta != 0) atomicAdd(P.live + vb + (int)a_nbr(a), delta);
+    bool cross1 = false;
+    if (go && tl < L && delta != 0) {
+        const int old = atomicAdd(P.live + vb + (int)a_nbr(a), delta);
+        cross1 = delta < 0 && old > M && old + delta <= M;
+    }
+    // neighbours whose live counter crossed the segment's level downwards join the next round's low list
+    la.push(cross0, (unsigned int)(vb + (size_t)rawnbr));
+    la.push(cross1, (unsigned int)(vb + (size_t)a_nbr(a)));
     if (go && rawvalid) {
         if (P.o_v == 0 && ldcg_u8(P.state + vb + rawnbr) == 1) {
             int old = atomicSub(P.blk + vb + rawnbr, 1);
@@ -468,8 +524,8 @@ constexpr int FCAP = 8;   // fill entries per item that the chunk prologue stage
 // to the 32 / W tiles of the warp, 32 / W at a time.
 template <int W>
 __device__ void run_tier(const SchurParams& P, const RoundCtx& rc, unsigned mask, unsigned int my_idx, int my_b,
-                         int my_nb, int my_nfill, const uint64_t* fbuf, long long my_slot0, int my_nslots,
-                         LocalStats& ls, PendingPush& pend) {
+                         int my_nb, int my_nfill, const uint64_t* fbuf, long long my_slot0, int my_nslots, int my_M,
+                         LocalStats& ls, PendingPush& pend, LowAppender& la) {
     constexpr int TPW = 32 / W;
     const int lane = threadIdx.x & 31;
     const int tile = lane / W;
@@ -489,8 +545,9 @@ __device__ void run_tier(const SchurParams& P, const RoundCtx& rc, unsigned mask
         const int nfill = __shfl_sync(RLAP_FULL_MASK, my_nfill, sl);
         const long long sl0 = __shfl_sync(RLAP_FULL_MASK, my_slot0, sl);
         const int nsl = __shfl_sync(RLAP_FULL_MASK, my_nslots, sl);
+        const int M = __shfl_sync(RLAP_FULL_MASK, my_M, sl);
         if (src == 0xffffffffu) idx = 0xffffffffu;
-        eliminate_star_tile<W>(P, rc, idx, b, nb, fbuf + sl * FCAP, nfill, sl0, nsl, ls, pend);
+        eliminate_star_tile<W>(P, rc, idx, b, nb, fbuf + sl * FCAP, nfill, sl0, nsl, M, ls, pend, la);
         mask = rest;
     }
 }
@@ -498,7 +555,7 @@ __device__ void run_tier(const SchurParams& P, const RoundCtx& rc, unsigned mask
 // process work-list items [start, end): a warp takes a chunk of up to 32 items and serves them tier by
 // tier (8-, 16-, 32-lane register tiles, then the shared-memory path); big stars go to the block phase
 __device__ void run_warp_items(const SchurParams& P, const RoundCtx& rc, uint64_t* smem, CtaScratch* cs, int* next,
-                               int start, int end, LocalStats& ls) {
+                               int start, int end, LocalStats& ls, LowAppender& la) {
     const int gw = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int nw = (int)((gridDim.x * blockDim.x) >> 5);
     const int lane = threadIdx.x & 31;
@@ -536,7 +593,7 @@ __device__ void run_warp_items(const SchurParams& P, const RoundCtx& rc, uint64_
         const int end = my_end;
         const int it = c0 + lane;
         unsigned int idx = 0xffffffffu;
-        int lv = -1, cls = -1, b = 0, nb = 0, nfill = 0;
+        int lv = -1, cls = -1, b = 0, nb = 0, nfill = 0, M = -1;
         __syncwarp();   // the previous chunk is done with the staging buffer
         if (lane < chunk && it < end) {
             idx = __ldcg(P.wl + it);
@@ -545,6 +602,7 @@ __device__ void run_warp_items(const SchurParams& P, const RoundCtx& rc, uint64_
             if (P.o_v != 0) {  // truncated final round of a graph: only the highest ids go
                 size_t seg = (size_t)view * P.G + graph_of(P, v);
                 skip = ldcg_i32(P.ovfseg + seg) && idx < __ldcg(P.thresh + seg);
+                M = ldcg_i32(P.lvl + seg);
             }
             if (!skip) {
                 lv = ldcg_i32(P.live + idx);
@@ -608,16 +666,16 @@ __device__ void run_warp_items(const SchurParams& P, const RoundCtx& rc, uint64_
             }
         }
         PendingPush pend;
-        run_tier<8>(P, rc, m8, idx, b, nb, nfill, fbuf, slot0, nslots, ls, pend);
-        run_tier<16>(P, rc, m16, idx, b, nb, nfill, fbuf, slot0, nslots, ls, pend);
-        run_tier<32>(P, rc, m32, idx, b, nb, nfill, fbuf, slot0, nslots, ls, pend);
+        run_tier<8>(P, rc, m8, idx, b, nb, nfill, fbuf, slot0, nslots, M, ls, pend, la);
+        run_tier<16>(P, rc, m16, idx, b, nb, nfill, fbuf, slot0, nslots, M, ls, pend, la);
+        run_tier<32>(P, rc, m32, idx, b, nb, nfill, fbuf, slot0, nslots, M, ls, pend, la);
         pend.flush();
         __syncwarp();
         while (msm) {
             int k = __ffs(msm) - 1;
             msm &= msm - 1;
             unsigned int kidx = __shfl_sync(RLAP_FULL_MASK, idx, k);
-            eliminate_star<false>(P, rc, (int)(kidx / (unsigned)P.n), (int)(kidx % (unsigned)P.n), sb, cs, ls);
+            eliminate_star<false>(P, rc, (int)(kidx / (unsigned)P.n), (int)(kidx % (unsigned)P.n), sb, cs, ls, la);
         }
     }
 }
@@ -625,11 +683,11 @@ __device__ void run_warp_items(const SchurParams& P, const RoundCtx& rc, uint64_
 // deferred items [start, end): one block per item in shared memory; stars beyond CAP_CTA go to the
 // NSLOT blocks that own a global scratch slot
 __device__ void run_block_items(const SchurParams& P, const RoundCtx& rc, uint64_t* smem, CtaScratch* cs, int start,
-                                int end, LocalStats& ls) {
+                                int end, LocalStats& ls, LowAppender& la) {
     for (int it = start + (int)blockIdx.x; it < end; it += (int)gridDim.x) {
         unsigned int idx = __ldcg(P.dl + it);
         int view = (int)(idx / (unsigned)P.n), v = (int)(idx % (unsigned)P.n);
-        if (ldcg_i32(P.live + idx) <= CAP_CTA) eliminate_star<true>(P, rc, view, v, cta_buf(smem), cs, ls);
+        if (ldcg_i32(P.live + idx) <= CAP_CTA) eliminate_star<true>(P, rc, view, v, cta_buf(smem), cs, ls, la);
         __syncthreads();
     }
     if ((int)blockIdx.x < NSLOT) {
@@ -639,7 +697,7 @@ __device__ void run_block_items(const SchurParams& P, const RoundCtx& rc, uint64
             if (ldcg_i32(P.live + idx) <= CAP_CTA) continue;
             if ((j++ % NSLOT) != (int)blockIdx.x) continue;
             int view = (int)(idx / (unsigned)P.n), v = (int)(idx % (unsigned)P.n);
-            eliminate_star<true>(P, rc, view, v, scratch_buf(P), cs, ls);
+            eliminate_star<true>(P, rc, view, v, scratch_buf(P), cs, ls, la);
             __syncthreads();
         }
     }
@@ -648,7 +706,8 @@ __device__ void run_block_items(const SchurParams& P, const RoundCtx& rc, uint64
 __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
     extern __shared__ __align__(16) uint64_t smem[];
     __shared__ CtaScratch cs;
-    __shared__ int s_next;
+    __shared__ int s_next, s_nsel;
+    __shared__ unsigned int s_lowbuf[WARPS_PER_BLOCK][LOWBUF];
     cg::grid_group grid = cg::this_grid();
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long nthr = (long long)gridDim.x * blockDim.x;
@@ -673,12 +732,14 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
         } else {
             P.state[idx] = (__ldg(P.ptr + v + 1) == __ldg(P.ptr + v)) ? 4 : 1;
             P.candround[idx] = -1;
+            P.rank[idx] = -1;   // degree / coarsen: round stamp of the low list
         }
     }
     if (!random_order) {
         for (long long s = tid; s < VG; s += nthr) {
             int g = (int)(s % P.G);
             P.rem[s] = __ldg(P.teff + g);
+            P.lvl[s] = -1;
             P.minkey[s] = 0x7fffffff;
             P.minkey[VG + s] = 0x7fffffff;
             P.cntI[s] = 0;
@@ -717,6 +778,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
     int rounds = 0;
     RoundCtx rc;
     LocalStats ls;
+    LowAppender la;
+    la.buf = s_lowbuf[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
     const unsigned uVN = (unsigned)VN, un = (unsigned)P.n;
@@ -775,12 +838,12 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
             if (tid == 0) { P.ctr[CTR_WCNT0 + (rounds + 1) % 3] = 0; P.ctr[CTR_DCNT0 + (rounds + 1) % 3] = 0; }
             rc.wl_base = wl_end; rc.wslot = CTR_WCNT0 + rounds % 3;
             rc.dl_base = dl_start; rc.dslot = CTR_DCNT0 + rounds % 3;
-            run_warp_items(P, rc, smem, &cs, &s_next, wl_start, wl_end, ls);
+            run_warp_items(P, rc, smem, &cs, &s_next, wl_start, wl_end, ls, la);
             wl_start = wl_end;
             gsync(ST_T_D1);
             int dl_end = dl_start + ldcg_i32(P.ctr + rc.dslot);
             if (dl_end != dl_start) {
-                run_block_items(P, rc, smem, &cs, dl_start, dl_end, ls);
+                run_block_items(P, rc, smem, &cs, dl_start, dl_end, ls, la);
                 dl_start = dl_end;
                 gsync(ST_T_D2);
             }
@@ -788,77 +851,158 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
         }
     } else {
         lap(ST_T_INIT);
-        // degree / coarsen: rounds over the minimum-key bucket of every (view, graph) segment
+        // degree / coarsen: rounds over the minimum-key bucket of every (view, graph) segment.
+        // Full scans of the vertices are only made when a segment's level advances: lvl[seg] is the minimum key
+        // the last full scan found, and every alive vertex whose key is <= lvl[seg] is on the round's low list
+        // (bucket members that were blocked, listed vertices that were not in the bucket, and every vertex whose
+        // live counter was seen crossing from above lvl to lvl or below by the elimination phase). While the low
+        // list of a segment has an entry in play the bucket is taken from the list alone.
+        constexpr int SEG_SM = 1024, WBUF = 320;
+        const int INF = 0x7fffffff;
+        int* mkl = P.minkey;          // minimum over the low list
+        int* mks = P.minkey + VG;     // minimum over a full scan
+        const bool bsm = VG <= (long long)SEG_SM;
         while (true) {
             const int par = rounds & 1;
-            int* mk = P.minkey + (size_t)par * VG;
-            int* mk_other = P.minkey + (size_t)(par ^ 1) * VG;
+            const unsigned int* low_in = P.low + (size_t)par * (size_t)P.low_cap;
+            la.dst = P.low + (size_t)(par ^ 1) * (size_t)P.low_cap;
+            la.cap = P.low_cap;
+            la.tail = P.ctr + CTR_LOW0 + (par ^ 1);
+            la.ovf = P.ctr + CTR_LOWOVF0 + (par ^ 1);
+            long long n_in = ldcg_i32(P.ctr + CTR_LOW0 + par);
+            if (n_in > P.low_cap) n_in = P.low_cap;
+            if (ldcg_i32(P.ctr + CTR_LOWOVF0 + par)) n_in = 0;   // entries were lost: every segment rescans
             rc.wl_base = wl_start; rc.wslot = CTR_WCNT0 + rounds % 3;
             rc.dl_base = dl_start; rc.dslot = CTR_DCNT0 + rounds % 3;
-            // phase A: minimum key per segment
             if (tid == 0) {
                 P.ctr[CTR_ACTIVE0 + (par ^ 1)] = 0; P.ctr[CTR_OVF0 + (par ^ 1)] = 0;
                 P.ctr[CTR_WCNT0 + (rounds + 1) % 3] = 0; P.ctr[CTR_DCNT0 + (rounds + 1) % 3] = 0;
+                P.ctr[CTR_LOW0 + (par ^ 1)] = 0; P.ctr[CTR_LOWOVF0 + (par ^ 1)] = 0;
             }
-            for (long long s = tid; s < VG; s += nthr) { mk_other[s] = 0x7fffffff; P.cntI[s] = 0; P.ovfseg[s] = 0; }
+            for (long long s = tid; s < VG; s += nthr) { P.cntI[s] = 0; P.ovfseg[s] = 0; }
+            // ---- phase A1: minimum key over the low-list entries in play
             {
-                // the star buffers are idle during this phase: per-segment minima are reduced in shared memory and
-                // the per-segment `rem` values are read from a shared copy (every warp of the grid asking L2 for
-                // the same one or two lines is a hot spot)
-                int* smin = (int*)smem;
-                int* srem = smin + VG;
-                const bool use_smem = VG <= (long long)(3 * CAP_CTA);
-                if (use_smem) {
-                    for (int q = threadIdx.x; q < (int)VG; q += blockDim.x) { smin[q] = 0x7fffffff; srem[q] = ldcg_i32(P.rem + q); }
-                    __syncthreads();
-                }
                 bool any = false;
-                // four independent elements per thread and iteration; every load is issued before the first use,
-                // so one memory round trip serves four vertices
-                // (view, vertex) of the running index are advanced incrementally: no division in the loop
-                const unsigned step_q = (unsigned)nthr / un, step_r = (unsigned)nthr % un;
-                unsigned cview = (unsigned)tid / un, cv = (unsigned)tid % un;
-                for (unsigned base = (unsigned)(tid - lane); base < uVN; base += 4u * (unsigned)nthr) {
-                    uint8_t st4[4];
-                    int lv4[4], rm4[4], sg4[4];
-#pragma unroll
-                    for (int q4 = 0; q4 < 4; q4++) {
-                        const unsigned idx = base + (unsigned)q4 * (unsigned)nthr + lane;
-                        st4[q4] = 2; lv4[q4] = 0; rm4[q4] = 0; sg4[q4] = 0;
-                        const int view = (int)cview, v = (int)cv;
-                        cview += step_q; cv += step_r;
-                        if (cv >= un) { cv -= un; cview++; }
-                        if (idx < uVN) {
-                            sg4[q4] = view * P.G + graph_of(P, v);
-                            st4[q4] = ldcg_u8(P.state + idx);
-                            lv4[q4] = ldcg_i32(P.live + idx);
-                            rm4[q4] = use_smem ? srem[sg4[q4]] : ldcg_i32(P.rem + sg4[q4]);
+                for (long long i0 = tid - lane; i0 < n_in; i0 += nthr) {
+                    const long long i = i0 + lane;
+                    bool valid = false;
+                    int seg = 0, key = INF;
+                    if (i < n_in) {
+                        const unsigned idx = __ldcg(low_in + i);
+                        const uint8_t st = ldcg_u8(P.state + idx);
+                        if (st != 2) {
+                            seg = (int)(idx / un) * P.G + graph_of(P, (int)(idx % un));
+                            key = (st == 4) ? 0 : max(ldcg_i32(P.live + idx), 1);
+                            valid = ldcg_i32(P.rem + seg) > 0 && key <= ldcg_i32(P.lvl + seg);
                         }
                     }
-#pragma unroll
-                    for (int q4 = 0; q4 < 4; q4++) {
-                        const bool valid = st4[q4] != 2 && rm4[q4] > 0;
-                        const int seg = sg4[q4];
-                        const int key = valid ? ((st4[q4] == 4) ? 0 : max(lv4[q4], 1)) : 0x7fffffff;
-                        unsigned vm = __ballot_sync(RLAP_FULL_MASK, valid);
-                        if (vm == 0) continue;
-                        any = true;
-                        int leader = __ffs(vm) - 1;
-                        int seg0 = __shfl_sync(RLAP_FULL_MASK, seg, leader);
-                        bool same = __all_sync(RLAP_FULL_MASK, !valid || seg == seg0);
-                        if (same) {
-                            int k = __reduce_min_sync(RLAP_FULL_MASK, key);
-                            if (lane == leader) { if (use_smem) atomicMin(smin + seg0, k); else atomicMin(mk + seg0, k); }
-                        } else if (valid) {
-                            if (use_smem) atomicMin(smin + seg, key); else atomicMin(mk + seg, key);
-                        }
+                    const unsigned vm = __ballot_sync(RLAP_FULL_MASK, valid);
+                    if (vm == 0) continue;
+                    any = true;
+                    const int leader = __ffs(vm) - 1;
+                    const int seg0 = __shfl_sync(RLAP_FULL_MASK, seg, leader);
+                    if (__all_sync(RLAP_FULL_MASK, !valid || seg == seg0)) {
+                        const int k = __reduce_min_sync(RLAP_FULL_MASK, valid ? key : INF);
+                        if (lane == leader) atomicMin(mkl + seg0, k);
+                    } else if (valid) {
+                        atomicMin(mkl + seg, key);
                     }
                 }
-                if (use_smem) {
+                if (any && lane == 0) P.ctr[CTR_ACTIVE0 + par] = 1;
+            }
+            gsync(ST_T_A);
+            if ((P.flags & 512) && tid == 0) {   // debug: list size and number of rescanning segments per round
+                int ns = 0, mn = INF;
+                for (long long q = 0; q < VG; q++) {
+                    if (ldcg_i32(P.rem + q) > 0 && ldcg_i32(mkl + q) == INF) ns++;
+                    mn = min(mn, ldcg_i32(mkl + q));
+                }
+                printf("round %d: low list %lld entries, %d of %lld segments rescan, min list key %d, lvl[0] %d rem[0] %d\n",
+                       rounds, n_in, ns, VG, mn, P.lvl[0], P.rem[0]);
+            }
+            // ---- phase A2: segments with nothing in play on the list scan all their vertices for the minimum key
+            {
+                int* smin = (int*)smem;         // [VG] block-level minima
+                int* sneed = smin + SEG_SM;     // [VG] 1 = the segment rescans
+                int* sviews = sneed + SEG_SM;   // views with a rescanning segment (the scan visits only their vertices)
+                int* sflag = sviews + SEG_SM;
+                unsigned nsel = (unsigned)P.V;
+                if (bsm) {
+                    for (int q = threadIdx.x; q < P.V; q += blockDim.x) sflag[q] = 0;
+                    if (threadIdx.x == 0) s_nsel = 0;
                     __syncthreads();
                     for (int q = threadIdx.x; q < (int)VG; q += blockDim.x) {
-                        int k = smin[q];
-                        if (k != 0x7fffffff) atomicMin(mk + q, k);
+                        smin[q] = INF;
+                        const int need = (ldcg_i32(P.rem + q) > 0 && ldcg_i32(mkl + q) == INF) ? 1 : 0;
+                        sneed[q] = need;
+                        if (need) sflag[q / P.G] = 1;
+                    }
+                    __syncthreads();
+                    // ascending view order: every block must enumerate the selected vertices identically
+                    for (int q = threadIdx.x; q < P.V; q += blockDim.x) {
+                        if (sflag[q]) {
+                            int pos = 0;
+                            for (int j = 0; j < q; j++) pos += sflag[j];
+                            sviews[pos] = q;
+                            atomicAdd(&s_nsel, 1);
+                        }
+                    }
+                    __syncthreads();
+                    nsel = (unsigned)s_nsel;
+                }
+                bool any = false;
+                // four independent elements per thread and iteration; every load is issued before the first use;
+                // (selected view, vertex) of the running index are advanced incrementally: no division in the loop
+                const unsigned total = nsel * un;
+                const unsigned step_q = (unsigned)nthr / un, step_r = (unsigned)nthr % un;
+                unsigned cview = (unsigned)tid / un, cv = (unsigned)tid % un;
+                for (unsigned base = (unsigned)(tid - lane); base < total; base += 4u * (unsigned)nthr) {
+                    uint8_t st4[4];
+                    int lv4[4], sg4[4];
+                    bool nd4[4];
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; q4++) {
+                        const unsigned e = base + (unsigned)q4 * (unsigned)nthr + lane;
+                        st4[q4] = 2; lv4[q4] = 0; sg4[q4] = 0; nd4[q4] = false;
+                        const unsigned sv = cview;
+                        const int v = (int)cv;
+                        cview += step_q; cv += step_r;
+                        if (cv >= un) { cv -= un; cview++; }
+                        if (e < total) {
+                            const int view = bsm ? sviews[sv] : (int)sv;
+                            const unsigned idx = (unsigned)view * un + (unsigned)v;
+                            sg4[q4] = view * P.G + graph_of(P, v);
+                            nd4[q4] = bsm ? (sneed[sg4[q4]] != 0)
+                                          : (ldcg_i32(P.rem + sg4[q4]) > 0 && ldcg_i32(mkl + sg4[q4]) == INF);
+                            if (nd4[q4]) {
+                                st4[q4] = ldcg_u8(P.state + idx);
+                                lv4[q4] = ldcg_i32(P.live + idx);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; q4++) {
+                        const bool valid = nd4[q4] && st4[q4] != 2;
+                        const int seg = sg4[q4];
+                        const int key = valid ? ((st4[q4] == 4) ? 0 : max(lv4[q4], 1)) : INF;
+                        const unsigned vm = __ballot_sync(RLAP_FULL_MASK, valid);
+                        if (vm == 0) continue;
+                        any = true;
+                        const int leader = __ffs(vm) - 1;
+                        const int seg0 = __shfl_sync(RLAP_FULL_MASK, seg, leader);
+                        if (__all_sync(RLAP_FULL_MASK, !valid || seg == seg0)) {
+                            const int k = __reduce_min_sync(RLAP_FULL_MASK, key);
+                            if (lane == leader) { if (bsm) atomicMin(smin + seg0, k); else atomicMin(mks + seg0, k); }
+                        } else if (valid) {
+                            if (bsm) atomicMin(smin + seg, key); else atomicMin(mks + seg, key);
+                        }
+                    }
+                }
+                if (bsm) {
+                    __syncthreads();
+                    for (int q = threadIdx.x; q < (int)VG; q += blockDim.x) {
+                        const int k = smin[q];
+                        if (k != INF) atomicMin(mks + q, k);
                     }
                     __syncthreads();
                 }
@@ -866,22 +1010,56 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
             }
             gsync(ST_T_A);
             if (ldcg_i32(P.ctr + CTR_ACTIVE0 + par) == 0) break;
-            // phase B: members of the minimum bucket with no bucket neighbour of higher id
-            // shared memory during this phase (the star buffers are idle): per-segment rem / min-key copies and
-            // candidate counters (if there are few enough segments), and a candidate buffer per warp so that the
-            // work-list tail is bumped once per ~500 candidates instead of once per warp ballot
-            constexpr int SEG_SM = 1024, WBUF = 512;
-            int* srem = (int*)smem;
-            int* smk = srem + SEG_SM;
-            int* scnt = smk + SEG_SM;
-            unsigned int* wbuf = (unsigned int*)((int*)smem + 4096) + (size_t)(threadIdx.x >> 5) * WBUF;
+            if (rounds > P.n + 8) { if (tid == 0) set_status(P, 10); break; }   // every round removes a vertex of every active segment
+            // ---- phase B: members of the minimum bucket with no bucket neighbour of higher id are selected, the
+            // other members (and the listed vertices below the level that are not in the bucket) go to the next list.
+            // Shared memory (the star buffers are idle): per-segment copies if there are few enough segments, a
+            // candidate buffer per warp so that the work-list tail is bumped once per few hundred candidates.
+            int* srem = (int*)smem;                 // remaining removals (0: the segment is done)
+            int* smk = srem + SEG_SM;               // bucket key of the round (INF: nothing to do)
+            int* scnt = smk + SEG_SM;               // candidates selected by this block
+            int* slv = scnt + SEG_SM;               // level; -1 marks a segment that rescans in this round
+            int* sviews = slv + SEG_SM;             // views with a segment that rescans in this round
+            int* sflag = sviews + SEG_SM;
+            unsigned int* wbuf = (unsigned int*)((int*)smem + 6 * SEG_SM) + (size_t)(threadIdx.x >> 5) * WBUF;
             int wfill = 0;
-            const bool bsm = VG <= (long long)SEG_SM;
+            unsigned nselB = (unsigned)P.V;
+            // per-segment view of the round: bucket key m, scan flag, level
+            auto seg_round = [&](int seg, int& rm, int& m, bool& scan, int& lv) {
+                if (bsm) {
+                    rm = srem[seg]; m = smk[seg]; lv = slv[seg]; scan = lv < 0;
+                } else {
+                    rm = ldcg_i32(P.rem + seg);
+                    const int ml = ldcg_i32(mkl + seg);
+                    scan = ml == INF;
+                    m = scan ? ldcg_i32(mks + seg) : ml;
+                    lv = scan ? -1 : ldcg_i32(P.lvl + seg);
+                }
+            };
             if (bsm) {
+                for (int q = threadIdx.x; q < P.V; q += blockDim.x) sflag[q] = 0;
+                if (threadIdx.x == 0) s_nsel = 0;
+                __syncthreads();
                 for (int q = threadIdx.x; q < (int)VG; q += blockDim.x) {
-                    srem[q] = ldcg_i32(P.rem + q); smk[q] = ldcg_i32(mk + q); scnt[q] = 0;
+                    const int ml = ldcg_i32(mkl + q);
+                    const bool scan = ml == INF;
+                    srem[q] = ldcg_i32(P.rem + q);
+                    smk[q] = scan ? ldcg_i32(mks + q) : ml;
+                    slv[q] = scan ? -1 : ldcg_i32(P.lvl + q);
+                    scnt[q] = 0;
+                    if (scan && srem[q] > 0 && smk[q] != INF) sflag[q / P.G] = 1;
                 }
                 __syncthreads();
+                for (int q = threadIdx.x; q < P.V; q += blockDim.x) {   // ascending view order, identical in every block
+                    if (sflag[q]) {
+                        int pos = 0;
+                        for (int j = 0; j < q; j++) pos += sflag[j];
+                        sviews[pos] = q;
+                        atomicAdd(&s_nsel, 1);
+                    }
+                }
+                __syncthreads();
+                nselB = (unsigned)s_nsel;
             }
             auto flush = [&]() {
                 if (wfill == 0) return;
@@ -893,82 +1071,132 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
                 __syncwarp();
                 wfill = 0;
             };
-            const unsigned step_q = (unsigned)nthr / un, step_r = (unsigned)nthr % un;
-            unsigned cview = (unsigned)tid / un, cv = (unsigned)tid % un;
-            for (unsigned base = (unsigned)(tid - lane); base < uVN; base += 4u * (unsigned)nthr) {
-                uint8_t st4[4];
-                int lv4[4], rm4[4], sg4[4], mk4[4], vw4[4], vx4[4];
+            // bucket member v of `view` (key m): true if no alive neighbour of higher id has key m
+            auto member_free = [&](unsigned idx, int view, int v, int m) -> bool {
+                const size_t vb = (size_t)view * P.n;
+                bool ok = true;
+                // base neighbours, four at a time: ids first, then states and live counters together
+                const int pb = __ldg(P.ptr + v), pe = __ldg(P.ptr + v + 1);
+                for (int p = pb; p < pe && ok; p += 4) {
+                    int u4[4];
 #pragma unroll
-                for (int q4 = 0; q4 < 4; q4++) {
-                    const unsigned idx = base + (unsigned)q4 * (unsigned)nthr + lane;
-                    st4[q4] = 2; lv4[q4] = 0; rm4[q4] = 0; sg4[q4] = 0; mk4[q4] = -1;
-                    const int view = (int)cview, v = (int)cv;
-                    vw4[q4] = view; vx4[q4] = v;
-                    cview += step_q; cv += step_r;
-                    if (cv >= un) { cv -= un; cview++; }
-                    if (idx < uVN) {
-                        sg4[q4] = view * P.G + graph_of(P, v);
-                        st4[q4] = ldcg_u8(P.state + idx);
-                        lv4[q4] = ldcg_i32(P.live + idx);
-                        rm4[q4] = bsm ? srem[sg4[q4]] : ldcg_i32(P.rem + sg4[q4]);
-                        mk4[q4] = bsm ? smk[sg4[q4]] : ldcg_i32(mk + sg4[q4]);
+                    for (int k = 0; k < 4; k++) u4[k] = (p + k < pe) ? __ldg(P.col + p + k) : -1;
+                    uint8_t s4[4];
+                    int l4[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        s4[k] = 2; l4[k] = 0;
+                        if (u4[k] > v) { s4[k] = ldcg_u8(P.state + vb + u4[k]); l4[k] = ldcg_i32(P.live + vb + u4[k]); }
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        if (u4[k] > v && s4[k] != 2 && max(l4[k], 1) == m) ok = false;
+                }
+                const int4* pool = P.pool + (size_t)view * (size_t)P.pool_cap;
+                for (int p = ldcg_i32(P.head + idx); p >= 0 && ok;) {
+                    int4 en = __ldcg(pool + p);
+                    if (en.x > v) {
+                        uint8_t su = ldcg_u8(P.state + vb + en.x);
+                        int lu = ldcg_i32(P.live + vb + en.x);
+                        if (su != 2 && max(lu, 1) == m) ok = false;
+                    }
+                    p = en.z;
+                }
+                return ok;
+            };
+            // warp-collective: record the selected members (`cand`) of one pass over 32 vertices
+            auto select = [&](bool cand, unsigned idx, int seg, int rm) {
+                const unsigned cm = __ballot_sync(RLAP_FULL_MASK, cand);
+                if (cm == 0) return;
+                if (wfill + 32 > WBUF) flush();
+                if (cand) {
+                    P.candround[idx] = rounds;
+                    wbuf[wfill + __popc(cm & lt)] = idx;
+                    if (bsm) {
+                        atomicAdd(scnt + seg, 1);
+                    } else {
+                        int c = atomicAdd(P.cntI + seg, 1);
+                        if (c + 1 > rm) P.ctr[CTR_OVF0 + par] = 1;
                     }
                 }
-#pragma unroll
-                for (int q4 = 0; q4 < 4; q4++) {
-                    const unsigned idx = base + (unsigned)q4 * (unsigned)nthr + lane;
-                    const int seg = sg4[q4], rm = rm4[q4], m = mk4[q4];
-                    bool cand = false;
-                    if (st4[q4] != 2 && rm > 0 && ((st4[q4] == 4) ? 0 : max(lv4[q4], 1)) == m) {
-                        const int view = vw4[q4], v = vx4[q4];
-                        const size_t vb = (size_t)view * P.n;
-                        bool ok = true;
-                        // base neighbours, four at a time: ids first, then states and live counters together
-                        const int pb = __ldg(P.ptr + v), pe = __ldg(P.ptr + v + 1);
-                        for (int p = pb; p < pe && ok; p += 4) {
-                            int u4[4];
-#pragma unroll
-                            for (int k = 0; k < 4; k++) u4[k] = (p + k < pe) ? __ldg(P.col + p + k) : -1;
-                            uint8_t s4[4];
-                            int l4[4];
-#pragma unroll
-                            for (int k = 0; k < 4; k++) {
-                                s4[k] = 2; l4[k] = 0;
-                                if (u4[k] > v) { s4[k] = ldcg_u8(P.state + vb + u4[k]); l4[k] = ldcg_i32(P.live + vb + u4[k]); }
-                            }
-#pragma unroll
-                            for (int k = 0; k < 4; k++)
-                                if (u4[k] > v && s4[k] != 2 && max(l4[k], 1) == m) ok = false;
-                        }
-                        const int4* pool = P.pool + (size_t)view * (size_t)P.pool_cap;
-                        for (int p = ldcg_i32(P.head + idx); p >= 0 && ok;) {
-                            int4 en = __ldcg(pool + p);
-                            if (en.x > v) {
-                                uint8_t su = ldcg_u8(P.state + vb + en.x);
-                                int lu = ldcg_i32(P.live + vb + en.x);
-                                if (su != 2 && max(lu, 1) == m) ok = false;
-                            }
-                            p = en.z;
-                        }
-                        cand = ok;
-                    }
-                    unsigned cm = __ballot_sync(RLAP_FULL_MASK, cand);
-                    if (cm == 0) continue;
-                    if (wfill + 32 > WBUF) flush();
-                    if (cand) {
-                        P.candround[idx] = rounds;
-                        wbuf[wfill + __popc(cm & lt)] = idx;
-                        if (bsm) {
-                            atomicAdd(scnt + seg, 1);
-                        } else {
-                            int c = atomicAdd(P.cntI + seg, 1);
-                            if (c + 1 > rm) P.ctr[CTR_OVF0 + par] = 1;
+                wfill += __popc(cm);
+            };
+            // B1: the low list (segments that do not rescan)
+            for (long long i0 = tid - lane; i0 < n_in; i0 += nthr) {
+                const long long i = i0 + lane;
+                bool cand = false, keep = false;
+                unsigned idx = 0;
+                int seg = 0, rm = 0;
+                if (i < n_in) {
+                    idx = __ldcg(low_in + i);
+                    const uint8_t st = ldcg_u8(P.state + idx);
+                    if (st != 2) {
+                        const int view = (int)(idx / un), v = (int)(idx % un);
+                        seg = view * P.G + graph_of(P, v);
+                        int m, lv;
+                        bool scan;
+                        seg_round(seg, rm, m, scan, lv);
+                        const int key = (st == 4) ? 0 : max(ldcg_i32(P.live + idx), 1);
+                        // in play, and the first copy of this vertex on the list (P.rank holds the round stamp)
+                        if (rm > 0 && !scan && key <= lv && atomicExch(P.rank + idx, rounds) != rounds) {
+                            if (key == m && member_free(idx, view, v, m)) cand = true; else keep = true;
                         }
                     }
-                    wfill += __popc(cm);
+                }
+                select(cand, idx, seg, rm);
+                la.push(keep, idx);
+            }
+            // B2: full scan of the segments that rescan; the level moves to the bucket key found
+            for (long long q = tid; q < VG; q += nthr) {
+                if (ldcg_i32(mkl + q) == INF) { const int m2 = ldcg_i32(mks + q); if (m2 != INF) P.lvl[q] = m2; }
+            }
+            {
+                const unsigned total = nselB * un;
+                const unsigned step_q = (unsigned)nthr / un, step_r = (unsigned)nthr % un;
+                unsigned cview = (unsigned)tid / un, cv = (unsigned)tid % un;
+                for (unsigned base = (unsigned)(tid - lane); base < total; base += 4u * (unsigned)nthr) {
+                    uint8_t st4[4];
+                    int lv4[4], rm4[4], sg4[4], mk4[4], vw4[4], vx4[4];
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; q4++) {
+                        const unsigned e = base + (unsigned)q4 * (unsigned)nthr + lane;
+                        st4[q4] = 2; lv4[q4] = 0; rm4[q4] = 0; sg4[q4] = 0; mk4[q4] = -1;
+                        const unsigned sv = cview;
+                        const int v = (int)cv;
+                        vw4[q4] = 0; vx4[q4] = v;
+                        cview += step_q; cv += step_r;
+                        if (cv >= un) { cv -= un; cview++; }
+                        if (e < total) {
+                            const int view = bsm ? sviews[sv] : (int)sv;
+                            vw4[q4] = view;
+                            const unsigned idx = (unsigned)view * un + (unsigned)v;
+                            sg4[q4] = view * P.G + graph_of(P, v);
+                            int lvq;
+                            bool scan;
+                            seg_round(sg4[q4], rm4[q4], mk4[q4], scan, lvq);
+                            if (scan && rm4[q4] > 0 && mk4[q4] != INF) {
+                                st4[q4] = ldcg_u8(P.state + idx);
+                                lv4[q4] = ldcg_i32(P.live + idx);
+                            } else {
+                                mk4[q4] = -1;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; q4++) {
+                        const unsigned idx = (unsigned)vw4[q4] * un + (unsigned)vx4[q4];
+                        const int m = mk4[q4];
+                        bool cand = false, keep = false;
+                        if (m >= 0 && st4[q4] != 2 && ((st4[q4] == 4) ? 0 : max(lv4[q4], 1)) == m) {
+                            if (member_free(idx, vw4[q4], vx4[q4], m)) cand = true; else keep = true;
+                        }
+                        select(cand, idx, sg4[q4], rm4[q4]);
+                        la.push(keep, idx);
+                    }
                 }
             }
             flush();
+            la.flush();
             if (bsm) {
                 __syncthreads();
                 for (int q = threadIdx.x; q < (int)VG; q += blockDim.x) {
@@ -1051,20 +1279,23 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
                 }
                 gsync(ST_T_C);
             }
-            // the truncated count is what phase D will eliminate
+            // the truncated count is what phase D will eliminate; the per-round minima are reset for the next round
             for (long long q = tid; q < VG; q += nthr) {
                 int rm = ldcg_i32(P.rem + q), c = ldcg_i32(P.cntI + q);
                 if (c > 0) P.rem[q] = rm - min(rm, c);
+                mkl[q] = INF; mks[q] = INF;
             }
             // phase D: eliminate
             int wl_end = wl_start + ldcg_i32(P.ctr + rc.wslot);
-            run_warp_items(P, rc, smem, &cs, &s_next, wl_start, wl_end, ls);
+            run_warp_items(P, rc, smem, &cs, &s_next, wl_start, wl_end, ls, la);
             wl_start = wl_end;
+            la.flush();
             gsync(ST_T_D1);
             int dl_end = dl_start + ldcg_i32(P.ctr + rc.dslot);
             if (dl_end != dl_start) {
-                run_block_items(P, rc, smem, &cs, dl_start, dl_end, ls);
+                run_block_items(P, rc, smem, &cs, dl_start, dl_end, ls, la);
                 dl_start = dl_end;
+                la.flush();
                 gsync(ST_T_D2);
             }
             rounds++;

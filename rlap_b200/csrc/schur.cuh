@@ -29,9 +29,12 @@ enum {
     CTR_OVF0 = 9,        // degree mode: some segment selected more candidates than it may remove
     CTR_OVF1 = 10,
     CTR_ROUNDS = 11,
-    CTR_EMIT_DL = 12,    // emission: deferred list tail (segments for the block path)
-    CTR_EMIT_ML = 13,    // emission: mid list tail (33..512 entries, register path of k_emit_sort_mid)
-    CTR_COUNT = 16
+    CTR_EMIT_C0 = 12,    // emission: tails of the six size-class lists (12..17; the elimination is over by then)
+    CTR_LOW0 = 14,       // degree mode: low-list tails, by round parity
+    CTR_LOW1 = 15,
+    CTR_LOWOVF0 = 16,    // degree mode: the low list of that parity overflowed (every segment rescans)
+    CTR_LOWOVF1 = 17,
+    CTR_COUNT = 20
 };
 
 struct RoundCtx {
@@ -80,7 +83,8 @@ struct SchurParams {
     unsigned long long* pool_cursor;  // [V]
     // per (view, graph) segment state, indexed [view * G + g]   (degree / coarsen)
     int* rem;
-    int* minkey;       // [2][V*G]
+    int* lvl;          // key level established by the segment's last full scan (low lists)
+    int* minkey;       // [2][V*G]: minimum key of the round over the low list / over a full scan
     int* cntI;
     int* ovfseg;
     unsigned int* thresh;
@@ -88,6 +92,8 @@ struct SchurParams {
     // work lists (append-only over the whole run)
     unsigned int* wl;
     unsigned int* dl;
+    unsigned int* low;  // [2][low_cap] degree / coarsen: vertices whose key may be <= lvl (ping-pong by round parity)
+    long long low_cap;
     int* ctr;          // [CTR_COUNT]
     unsigned long long* stats;  // [ST_COUNT]
     // global scratch for stars larger than CAP_CTA: slot b = 3 * scratch_cap u64 for block b
