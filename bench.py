@@ -219,7 +219,9 @@ def run_ours(args):
         out, vp, st = ops.schur_views(g, t, O_V, O_N, num_views=V, seed=1234 + step, view_base=rank * V, dtype=None,
                                       return_stats=True)
         stats_acc.append(st)
-        launches["n"] += 12 + 10  # ingest: 12 kernel launches; views: setup, eliminate, 2+2 emission, 3 scan, gather
+        # ingest: 12 kernel launches; views: setup, eliminate, prep, base, scatter, sort_warp, 4 x sort_mid, sort_block,
+        # sort_big, 2 x 3 scan, export, copy
+        launches["n"] += 12 + 20
         return out, vp
 
     # e2e: what a training loop that prefetches views does. Pinned host edge_index in, packed rows out to pinned
@@ -323,7 +325,7 @@ def run_ours(args):
     # measured DRAM traffic of the same kernel from the committed ncu --set full capture (same workload and V)
     traffic = None
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_k_eliminate_traffic.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01b_k_eliminate_traffic.json")))
         if int(tj.get("views_per_launch", 0)) == V:
             traffic = float(tj["traffic_bytes_per_launch"])
     except Exception:

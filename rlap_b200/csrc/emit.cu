@@ -441,6 +441,7 @@ __global__ void __launch_bounds__(256) k_emit_copy(SchurParams P, int* out_row, 
         const int total = __shfl_sync(RLAP_FULL_MASK, rel + L, 31 < (VN - base - 1) ? 31 : (int)(VN - base - 1));
         if (idx >= VN) rel = total;
         const int v0 = (int)(base % P.n);
+#pragma unroll 4
         for (int o0 = 0; o0 < total; o0 += 32) {
             const int o = o0 + lane;
             // last lane i with rel_i <= o (rows of empty vertices are skipped: equal offsets resolve to the last one)
@@ -453,11 +454,11 @@ __global__ void __launch_bounds__(256) k_emit_copy(SchurParams P, int* out_row, 
             const long long ksrc = __shfl_sync(RLAP_FULL_MASK, src, lo);
             const int krel = __shfl_sync(RLAP_FULL_MASK, rel, lo);
             if (o < total) {
-                const uint64_t a = P.raw[ksrc + (o - krel)];
+                const uint64_t a = __ldcs((const unsigned long long*)P.raw + ksrc + (o - krel));   // read once
                 int v = v0 + lo;
                 while (v >= P.n) v -= P.n;   // the 32 vertices may straddle view boundaries (tiny graphs: several)
                 const long long w = dst0 + o;
-                if (out_row) { out_row[w] = (int)a_nbr(a); out_col[w] = v; out_w[w] = a_w(a); }
+                if (out_row) { __stcs(out_row + w, (int)a_nbr(a)); __stcs(out_col + w, v); __stcs(out_w + w, a_w(a)); }
                 if (out_f64) {
                     out_f64[w * 3 + 0] = (double)a_nbr(a);
                     out_f64[w * 3 + 1] = (double)v;

@@ -34,7 +34,8 @@ enum {
     CTR_LOW1 = 15,
     CTR_LOWOVF0 = 16,    // degree mode: the low list of that parity overflowed (every segment rescans)
     CTR_LOWOVF1 = 17,
-    CTR_COUNT = 20
+    CTR_STEAL0 = 18,     // elimination phase: cursor of the part of the work list any warp may fetch (18..20, by round % 3)
+    CTR_COUNT = 24
 };
 
 struct RoundCtx {
@@ -42,6 +43,7 @@ struct RoundCtx {
     int wslot;     // ctr index of this round's work-list counter
     int dl_base;
     int dslot;
+    int sslot;     // ctr index of this round's shared-tail cursor
 };
 enum { ST_FILLS = 0, ST_POOL_MAX = 1, ST_MAXSTAR = 2, ST_DEFERRED = 3, ST_RAW = 4,
        ST_T_INIT = 8, ST_T_A = 9, ST_T_B = 10, ST_T_C = 11, ST_T_D1 = 12, ST_T_D2 = 13,
