@@ -405,7 +405,7 @@ int rlap_schur_eliminate(int64_t n, int64_t nnz, const int32_t* csr_ptr, const i
         fprintf(stderr, "rlap timers (us): k_eliminate %.0f |", 0.0 + (double)(stats ? stats[7] : 0));
         for (int i = 0; i < 6; i++)
             fprintf(stderr, " %s %.0f (wait %.0f)", nm[i], hstats[ST_T_INIT + i] / 1e3, hstats[ST_W_INIT + i] / 1e3 / nwarps);
-        fprintf(stderr, "\n");
+        fprintf(stderr, " | stars on the shared-memory warp path %llu\n", hstats[ST_DEFERRED]);
     }
     {
         std::lock_guard<std::mutex> lk(g_layout_mutex);

@@ -136,18 +136,6 @@ __device__ __forceinline__ void push_entry(const SchurParams& P, size_t vb, int4
     if (LIVE) atomicAdd(P.live + vb + owner, 1);
 }
 
-// The two pool entries of a fill edge whose `next` fields are still on their way back from the list-head
-// exchanges. Writing them is deferred until the tile has issued the loads of its next star, so the warp never
-// waits for the exchange round trip (degree / coarsen: a grid barrier separates the writers of a list from its
-// readers; o_v = random flushes before its fence).
-struct PendingPush {
-    int4 e0, e1;
-    int4* p0 = nullptr;
-    __device__ __forceinline__ void flush() {
-        if (p0) { p0[0] = e0; p0[1] = e1; p0 = nullptr; }
-    }
-};
-
 // degree / coarsen: appends to the next round's low list through a small per-warp shared buffer, so that the list
 // tail is bumped once per few dozen entries. Every member is warp-collective.
 constexpr int LOWBUF = 64;
@@ -178,6 +166,23 @@ struct LowAppender {
         if (fill + 32 > LOWBUF) flush();
         if (pred) buf[fill + __popc(m & ((1u << (threadIdx.x & 31)) - 1u))] = val;
         fill += __popc(m);
+    }
+};
+
+// Results that are still on their way back when a register tile finishes a star: the `next` fields of the two pool
+// entries of its fill edge (from the list-head exchanges) and the old value of the live counter it decremented.
+// Consuming them is deferred until the tile has issued the loads of its next star, so the warp does not wait for
+// those round trips (degree / coarsen: a grid barrier separates the writers of a list from its readers; o_v =
+// random flushes before its fence).
+struct PendingPush {
+    int4 e0, e1;
+    int4* p0 = nullptr;
+    int lo_old = 0, lo_lim = 0, lo_M = 0x7fffffff;   // crossing test: lo_M < lo_old <= lo_lim
+    unsigned int lo_idx = 0;
+    __device__ __forceinline__ void flush(LowAppender& la) {   // warp-collective
+        if (p0) { p0[0] = e0; p0[1] = e1; p0 = nullptr; }
+        la.push(lo_old > lo_M && lo_old <= lo_lim, lo_idx);
+        lo_M = 0x7fffffff;
     }
 };
 
@@ -216,7 +221,7 @@ __device__ __forceinline__ bool push_fill(const SchurParams& P, size_t vb, int4*
 }
 
 // Eliminate vertex v of `view` (A.2 clique sampling / A.4 coarsening / full clique), DESIGN.md §3.3.
-struct LocalStats { unsigned long long fills = 0, raw = 0; int maxstar = 0; };
+struct LocalStats { unsigned long long fills = 0, raw = 0; int maxstar = 0; unsigned nsm = 0; };
 
 template <bool CTA>
 __device__ void eliminate_star(const SchurParams& P, const RoundCtx& rc, int view, int v, StarBuf sb, CtaScratch* cs,
@@ -381,7 +386,7 @@ __device__ void eliminate_star_tile(const SchurParams& P, const RoundCtx& rc, un
     bool dead = false;
     if (a != RLAP_PAD_A) dead = ldcg_u8(P.state + vb + a_nbr(a)) == 2;
     // the previous star's pool entries: their `next` fields have arrived by now
-    pend.flush();
+    pend.flush(la);
     if (dead) a = RLAP_PAD_A;
     __syncwarp();
     const bool go = active && !fail;
@@ -486,16 +491,15 @@ __device__ void eliminate_star_tile(const SchurParams& P, const RoundCtx& rc, un
     }
     // o_v = random: pushes and dependency increments are ordered before the decrements;
     // the other orders separate rounds by grid barriers
-    if (P.o_v == 0) { pend.flush(); __threadfence(); }
+    if (P.o_v == 0) { pend.flush(la); __threadfence(); }
     __syncwarp();
-    bool cross1 = false;
+    // neighbours whose live counter crossed the segment's level downwards join the next round's low list; the test
+    // on the value the atomic returns is left to the next flush of `pend`
     if (go && tl < L && delta != 0) {
         const int old = atomicAdd(P.live + vb + (int)a_nbr(a), delta);
-        cross1 = delta < 0 && old > M && old + delta <= M;
+        if (delta < 0) { pend.lo_old = old; pend.lo_M = M; pend.lo_lim = M - delta; pend.lo_idx = (unsigned int)(vb + (size_t)a_nbr(a)); }
     }
-    // neighbours whose live counter crossed the segment's level downwards join the next round's low list
     la.push(cross0, (unsigned int)(vb + (size_t)rawnbr));
-    la.push(cross1, (unsigned int)(vb + (size_t)a_nbr(a)));
     if (go && rawvalid) {
         if (P.o_v == 0 && ldcg_u8(P.state + vb + rawnbr) == 1) {
             int old = atomicSub(P.blk + vb + rawnbr, 1);
@@ -669,8 +673,9 @@ __device__ void run_warp_items(const SchurParams& P, const RoundCtx& rc, uint64_
         run_tier<8>(P, rc, m8, idx, b, nb, nfill, fbuf, slot0, nslots, M, ls, pend, la);
         run_tier<16>(P, rc, m16, idx, b, nb, nfill, fbuf, slot0, nslots, M, ls, pend, la);
         run_tier<32>(P, rc, m32, idx, b, nb, nfill, fbuf, slot0, nslots, M, ls, pend, la);
-        pend.flush();
+        pend.flush(la);
         __syncwarp();
+        if (lane == 0) ls.nsm += (unsigned)__popc(msm);
         while (msm) {
             int k = __ffs(msm) - 1;
             msm &= msm - 1;
@@ -1306,6 +1311,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
         atomicAdd(P.stats + ST_FILLS, ls.fills);
         atomicAdd(P.stats + ST_RAW, ls.raw);
         atomicMax(P.stats + ST_MAXSTAR, (unsigned long long)ls.maxstar);
+        if (ls.nsm) atomicAdd(P.stats + ST_DEFERRED, (unsigned long long)ls.nsm);
     }
 }
 

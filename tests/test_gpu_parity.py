@@ -204,3 +204,50 @@ def test_torch_dispatcher_op_schema():
     assert torch.equal(torch.ops.extension_cpp.identity.default(a=a), a)
     schema = str(torch.ops.extension_cpp.approximate_cholesky.default._schema)
     assert "Tensor edge_info, int num_nodes, int num_remove, str o_v, str o_n" in schema
+
+
+def test_dirty_workspace_and_pool_retry_are_harmless(oracle_port):
+    """the workspace is never assumed to be zero: results do not depend on what the allocator hands back (a failed
+    run used to leave unwritten pool slots for the emission to read), and a pool overflow is retried cleanly"""
+    import rlap_b200
+    from rlap_b200 import graphs
+    rng = np.random.default_rng(0)
+    n = 100
+    ei = graphs.barabasi_albert(n, 50, seed=1)
+    w = util.sym_weights(ei)
+    g = _gpu_graph(ei, w, n, None)
+    optr, ocol, ow = oracle_port.ingest(ei, w, n)
+    for o_v in ("random", "degree", "coarsen"):
+        for full in (True, False):
+            flags = oracle_port.FLAG_FULL_CLIQUE if full else 0
+            r0, c0, w0 = oracle_port.keyed_schur(optr, ocol, ow, 50, o_v, "asc", seed=7, flags=flags)
+            for rep in range(6):
+                junk = torch.randint(0, 255, (int(rng.integers(1, 48)) << 20,), dtype=torch.uint8, device="cuda")
+                del junk
+                # a pool of 64 entries always overflows first: the retry path runs on recycled memory
+                (row, col, wt), vp = rlap_b200.schur_views(g, 50, o_v, "asc", seed=7, full_clique=full, dtype=None,
+                                                           pool_cap=64 if rep % 2 else 0)
+                assert np.array_equal(row.cpu().numpy(), r0) and np.array_equal(col.cpu().numpy(), c0), (o_v, full, rep)
+                assert np.array_equal(wt.cpu().numpy().view(np.uint32), w0.view(np.uint32)), (o_v, full, rep)
+
+
+@pytest.mark.parametrize("o_v", ["degree", "coarsen"])
+def test_many_desynchronised_views_match_oracle(oracle_port, o_v):
+    """48 views of one graph run their bucket levels out of step (some rescan while others work from their low
+    lists); every checked view must still be the oracle's, bit for bit"""
+    import rlap_b200
+    from rlap_b200 import graphs
+    n = 20000
+    ei = graphs.barabasi_albert(n, 7, seed=5)
+    optr, ocol, ow = oracle_port.ingest(ei, None, n)
+    g = _gpu_graph(ei, None, n, None)
+    V = 48
+    (row, col, wt), vp, st = rlap_b200.schur_views(g, n // 2, o_v, "asc", num_views=V, seed=99, dtype=None,
+                                                   return_stats=True)
+    row, col, wt, vp = row.cpu().numpy(), col.cpu().numpy(), wt.cpu().numpy(), vp.numpy()
+    for v in (0, 1, 17, 31, 47):
+        r0, c0, w0 = oracle_port.keyed_schur(optr, ocol, ow, n // 2, o_v, "asc", seed=99, view=v)
+        s, e = vp[v], vp[v + 1]
+        assert e - s == r0.shape[0], (v, e - s, r0.shape[0])
+        assert np.array_equal(row[s:e], r0) and np.array_equal(col[s:e], c0), v
+        assert np.array_equal(wt[s:e].view(np.uint32), w0.view(np.uint32)), v
