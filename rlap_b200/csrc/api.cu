@@ -20,7 +20,9 @@ namespace rlap {
 cudaError_t launch_setup_graphs(int n, int G, const int* gptr, const long long* num_remove, int* gid, int* teff,
                                 cudaStream_t stream);
 cudaError_t eliminate_grid(int* blocks_out);
-cudaError_t launch_eliminate(const SchurParams& P, cudaStream_t stream);
+cudaError_t launch_eliminate(const SchurParams& P, cudaStream_t stream, int blocks_req);
+cudaError_t launch_combine_groups(int K, const int* gctr, const unsigned long long* gstats, int* ctr,
+                                  unsigned long long* stats, cudaStream_t stream);
 cudaError_t launch_emit_count(const SchurParams& P, long long* total_dev, cudaStream_t stream);
 cudaError_t launch_emit_write(const SchurParams& P, int* out_row, int* out_col, float* out_w, double* out_f64,
                               cudaStream_t stream);
@@ -215,7 +217,16 @@ struct SchurLayout {
     long long* total_dev;
     long long* viewptr_dev;   // [V+1]
     long long G, V, pool_cap, scratch_cap;
+    int* gctr;                 // [MAX_GROUPS][CTR_COUNT] control blocks of the view groups
+    unsigned long long* gstats; // [MAX_GROUPS][ST_COUNT]
+    uint64_t* gscratch;        // [MAX_GROUPS] scratch slots
 };
+
+// The views of one call are eliminated by up to MAX_GROUPS concurrent cooperative launches of k_eliminate, each on its
+// own share of the SMs and with its own grid barrier: views are independent, and a barrier over all of them makes
+// every phase of every view wait for the slowest chain of any view (45 % of the warp time in the single-launch
+// profile, profiles/README.md).
+constexpr int MAX_GROUPS = 64;
 
 static long long default_pool_cap(long long nnz) { return 2 * nnz + 4096; }
 static long long default_scratch_cap(long long n) {
@@ -240,6 +251,8 @@ static SchurLayout schur_layout(long long n, long long nnz, long long G, long lo
     P.V = (int)V;
     P.ctr = c.take<int>(CTR_COUNT);
     P.stats = c.take<unsigned long long>(ST_COUNT);
+    L.gctr = c.take<int>((size_t)MAX_GROUPS * CTR_COUNT);
+    L.gstats = c.take<unsigned long long>((size_t)MAX_GROUPS * ST_COUNT);
     L.total_dev = c.take<long long>(1);
     L.viewptr_dev = c.take<long long>((size_t)V + 1);
     L.gptr_dev = c.take<int>((size_t)G + 1);
@@ -268,12 +281,17 @@ static SchurLayout schur_layout(long long n, long long nnz, long long G, long lo
     P.cntI = c.take<int>(VG);
     P.ovfseg = c.take<int>(VG);
     P.thresh = c.take<unsigned int>(VG);
-    P.blockcnt = c.take<int>((VN + SEL_BLOCK - 1) / SEL_BLOCK + 1);
-    P.wl = c.take<unsigned int>(2 * VN + 1);
-    P.dl = c.take<unsigned int>(VN + 1);
+    // work lists and scratch: one region per view group inside each array (slack for MAX_GROUPS regions)
+    P.blockcnt = c.take<int>((VN + SEL_BLOCK - 1) / SEL_BLOCK + 2 * MAX_GROUPS + 2);
+    P.wl = c.take<unsigned int>(2 * VN + MAX_GROUPS + 1);
+    P.dl = c.take<unsigned int>(VN + MAX_GROUPS + 1);
     P.low_cap = (long long)(2 * VN + 64);
-    P.low = c.take<unsigned int>(2 * (size_t)P.low_cap);
-    P.scratch = c.take<uint64_t>((size_t)NSLOT * 3 * (size_t)scratch_cap);
+    P.low = c.take<unsigned int>(4 * VN + 128 * (size_t)MAX_GROUPS);
+    {
+        const long long groups = V < MAX_GROUPS ? V : MAX_GROUPS;
+        P.scratch = c.take<uint64_t>((size_t)groups * NSLOT * 3 * (size_t)scratch_cap);
+        L.gscratch = P.scratch;
+    }
     P.scratch_cap = (int)scratch_cap;
     P.blocksum = c.take<long long>((size_t)scan_blocks((long long)VN));
     P.gptr = L.gptr_dev;
@@ -351,7 +369,59 @@ int rlap_schur_eliminate(int64_t n, int64_t nnz, const int32_t* csr_ptr, const i
     static thread_local cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     if (!ev[0]) for (int i = 0; i < 3; i++) CK(cudaEventCreate(&ev[i]));
     CK(cudaEventRecord(ev[0], stream));
-    CK(launch_eliminate(P, stream));
+    {
+        // view groups: K concurrent cooperative launches, each on blocks / K blocks
+        int blocks = 0;
+        CK(eliminate_grid(&blocks));
+        long long K = 1;
+        if (const char* env = getenv("RLAP_GROUPS")) K = atoll(env);
+        else K = n_views / ((n_views + 31) / 32);        // at most 32 groups (about 9 blocks each), equal shares of views
+        if (K > n_views) K = n_views;
+        if (K > MAX_GROUPS) K = MAX_GROUPS;
+        if (K > blocks / 2) K = blocks / 2;
+        if (K < 1) K = 1;
+        if (K == 1) {
+            CK(launch_eliminate(P, stream, 0));
+        } else {
+            static thread_local cudaStream_t gs[MAX_GROUPS] = {nullptr};
+            static thread_local cudaEvent_t gev[MAX_GROUPS + 1] = {nullptr};
+            for (long long g = 0; g < K; g++) {
+                if (!gs[g]) CK(cudaStreamCreateWithFlags(&gs[g], cudaStreamNonBlocking));
+                if (!gev[g]) CK(cudaEventCreateWithFlags(&gev[g], cudaEventDisableTiming));
+            }
+            if (!gev[MAX_GROUPS]) CK(cudaEventCreateWithFlags(&gev[MAX_GROUPS], cudaEventDisableTiming));
+            CK(cudaMemsetAsync(L.gctr, 0, sizeof(int) * CTR_COUNT * (size_t)K, stream));
+            CK(cudaMemsetAsync(L.gstats, 0, sizeof(unsigned long long) * ST_COUNT * (size_t)K, stream));
+            CK(cudaEventRecord(gev[MAX_GROUPS], stream));
+            const long long G = n_graphs;
+            for (long long g = 0; g < K; g++) {
+                const long long v0 = n_views * g / K, v1 = n_views * (g + 1) / K, Vg = v1 - v0;
+                SchurParams Q = P;
+                const size_t o = (size_t)v0 * (size_t)n, og = (size_t)v0 * (size_t)G;
+                Q.V = (int)Vg;
+                Q.view_base = P.view_base + (uint32_t)v0;
+                Q.state += o; Q.live += o; Q.head += o; Q.rank += o; Q.blk += o; Q.candround += o;
+                Q.pool += (size_t)v0 * (size_t)P.pool_cap;
+                Q.pool_cursor += v0;
+                Q.rem += og; Q.lvl += og; Q.cntI += og; Q.ovfseg += og; Q.thresh += og;
+                Q.minkey += 2 * og;                                    // [2][Vg * G] inside the [2 * V * G] array
+                Q.blockcnt += o / SEL_BLOCK + 2 * (size_t)g;
+                Q.wl += 2 * o + (size_t)g;
+                Q.dl += o + (size_t)g;
+                Q.low += 4 * o + 128 * (size_t)g;
+                Q.low_cap = (long long)(2 * (size_t)Vg * (size_t)n + 64);
+                Q.scratch = L.gscratch + (size_t)g * NSLOT * 3 * (size_t)L.scratch_cap;
+                Q.ctr = L.gctr + (size_t)g * CTR_COUNT;
+                Q.stats = L.gstats + (size_t)g * ST_COUNT;
+                const int bg = (int)((long long)blocks * (g + 1) / K - (long long)blocks * g / K);
+                CK(cudaStreamWaitEvent(gs[g], gev[MAX_GROUPS], 0));
+                CK(launch_eliminate(Q, gs[g], bg));
+                CK(cudaEventRecord(gev[g], gs[g]));
+                CK(cudaStreamWaitEvent(stream, gev[g], 0));
+            }
+            CK(launch_combine_groups((int)K, L.gctr, L.gstats, P.ctr, P.stats, stream));
+        }
+    }
     if (getenv("RLAP_DEBUG_SYNC")) {
         cudaError_t de = cudaStreamSynchronize(stream);
         if (de != cudaSuccess) return cuda_fail(de, "k_eliminate (debug sync)");

@@ -695,12 +695,13 @@ __device__ void run_block_items(const SchurParams& P, const RoundCtx& rc, uint64
         if (ldcg_i32(P.live + idx) <= CAP_CTA) eliminate_star<true>(P, rc, view, v, cta_buf(smem), cs, ls, la);
         __syncthreads();
     }
-    if ((int)blockIdx.x < NSLOT) {
+    const int nslot = min(NSLOT, (int)gridDim.x);   // a view group may run on fewer blocks than there are slots
+    if ((int)blockIdx.x < nslot) {
         int j = 0;
         for (int it = start; it < end; it++) {
             unsigned int idx = __ldcg(P.dl + it);
             if (ldcg_i32(P.live + idx) <= CAP_CTA) continue;
-            if ((j++ % NSLOT) != (int)blockIdx.x) continue;
+            if ((j++ % nslot) != (int)blockIdx.x) continue;
             int view = (int)(idx / (unsigned)P.n), v = (int)(idx % (unsigned)P.n);
             eliminate_star<true>(P, rc, view, v, scratch_buf(P), cs, ls, la);
             __syncthreads();
@@ -1367,13 +1368,45 @@ cudaError_t eliminate_grid(int* blocks_out) {
     return cudaSuccess;
 }
 
-cudaError_t launch_eliminate(const SchurParams& P, cudaStream_t stream) {
+cudaError_t launch_eliminate(const SchurParams& P, cudaStream_t stream, int blocks_req) {
     int blocks = 0;
     cudaError_t e = eliminate_grid(&blocks);
     if (e != cudaSuccess) return e;
+    if (blocks_req > 0 && blocks_req < blocks) blocks = blocks_req;
     SchurParams Pc = P;
     void* args[] = {(void*)&Pc};
     return cudaLaunchCooperativeKernel((void*)k_eliminate, dim3(blocks), dim3(BLOCK_THREADS), args, kSmemBytes, stream);
+}
+
+// fold the control blocks of the view groups into the caller-visible one: first error, largest round count,
+// summed counters, longest phase times
+__global__ void k_combine_groups(int K, const int* gctr, const unsigned long long* gstats, int* ctr,
+                                 unsigned long long* stats) {
+    const int t = threadIdx.x;
+    if (t == 0) {
+        int status = 0, rounds = 0;
+        for (int g = 0; g < K; g++) {
+            const int* c = gctr + (size_t)g * CTR_COUNT;
+            if (status == 0) status = c[CTR_STATUS];
+            rounds = max(rounds, c[CTR_ROUNDS]);
+        }
+        ctr[CTR_STATUS] = status;
+        ctr[CTR_ROUNDS] = rounds;
+    }
+    if (t < ST_COUNT) {
+        unsigned long long acc = 0;
+        for (int g = 0; g < K; g++) {
+            const unsigned long long v = gstats[(size_t)g * ST_COUNT + t];
+            if (t == ST_MAXSTAR || t >= ST_T_INIT) acc = v > acc ? v : acc; else acc += v;
+        }
+        stats[t] = acc;
+    }
+}
+
+cudaError_t launch_combine_groups(int K, const int* gctr, const unsigned long long* gstats, int* ctr,
+                                  unsigned long long* stats, cudaStream_t stream) {
+    k_combine_groups<<<1, 32, 0, stream>>>(K, gctr, gstats, ctr, stats);
+    return cudaGetLastError();
 }
 
 }  // namespace rlap
