@@ -37,13 +37,6 @@ __global__ void k_emit_prep(SchurParams P) {
     cursor_of(P)[idx] = 0;
 }
 
-__device__ __forceinline__ void scatter_one(const SchurParams& P, size_t vb, int owner, int nbr, uint32_t wbits) {
-    if (P.state[vb + owner] == 2 || P.state[vb + nbr] == 2) return;
-    long long pos = P.rawoff[vb + owner] + atomicAdd(cursor_of(P) + vb + owner, 1);
-    if (pos < P.raw_cap) P.raw[pos] = ((uint64_t)(uint32_t)nbr << 32) | (uint64_t)wbits;
-    else set_status(P, 6);
-}
-
 // Base entries: an 8-lane tile per surviving vertex walks its (neighbour-ascending) CSR segment and writes the
 // entries whose neighbour is alive to the front of the vertex's staging segment, in order and without atomics;
 // rows longer than 64 are then served by the whole warp. cursor[v] = number of entries written.
@@ -105,8 +98,9 @@ __global__ void __launch_bounds__(256) k_emit_base(SchurParams P) {
     }
 }
 
-// Fill entries: grid-stride over the view's pool (blockIdx.y = view); an entry whose two endpoints are alive goes
-// behind the base entries of its owner
+// Fill entries: grid-stride over the view's pool (blockIdx.y = view), one thread per fill edge = the two entries
+// (j <- k), (k <- j) it left in adjacent slots (reservations are even, so pairs never straddle); if both endpoints
+// are alive each entry goes behind the base entries of its owner
 __global__ void __launch_bounds__(256) k_emit_scatter(SchurParams P) {
     if (run_failed(P)) return;
     const int view = blockIdx.y;
@@ -115,9 +109,19 @@ __global__ void __launch_bounds__(256) k_emit_scatter(SchurParams P) {
     long long used = (long long)P.pool_cursor[view];
     if (used > P.pool_cap) used = P.pool_cap;
     const int4* pool = P.pool + (size_t)view * (size_t)P.pool_cap;
-    for (long long e = t0; e < used; e += nt) {
-        int4 en = pool[e];
-        if (en.w >= 0) scatter_one(P, vb, en.w, en.x, (uint32_t)en.y);
+    for (long long e = 2 * t0; e + 1 < used; e += 2 * nt) {
+        const int4 e0 = __ldcs(pool + e);        // {k, w, next, j}
+        if (e0.w < 0) continue;                  // tombstones come in pairs as well
+        const int j = e0.w, k = e0.x;
+        if (P.state[vb + j] == 2 || P.state[vb + k] == 2) continue;
+        const long long p0 = P.rawoff[vb + j] + atomicAdd(cursor_of(P) + vb + j, 1);
+        const long long p1 = P.rawoff[vb + k] + atomicAdd(cursor_of(P) + vb + k, 1);
+        if (p0 < P.raw_cap && p1 < P.raw_cap) {
+            P.raw[p0] = ((uint64_t)(uint32_t)k << 32) | (uint64_t)(uint32_t)e0.y;
+            P.raw[p1] = ((uint64_t)(uint32_t)j << 32) | (uint64_t)(uint32_t)e0.y;
+        } else {
+            set_status(P, 6);
+        }
     }
 }
 
@@ -318,8 +322,31 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_emit_sort_warp(SchurParams
             off = P.rawoff[idx];
             if (lv == 0) P.outcnt[idx] = 0;
         }
-        // register path: one vertex at a time, all 32 lanes on its (contiguous) segment
-        unsigned small = __ballot_sync(RLAP_FULL_MASK, lv > 0 && lv <= 32);
+        // segments of at most 16 entries: two at a time, one per half warp (16-lane tiles, all shuffles tile-wide)
+        {
+            typedef Tile<16> T;
+            const int tile = lane >> 4, tl = lane & 15;
+            const unsigned tlt = (1u << tl) - 1u;
+            unsigned tiny = __ballot_sync(RLAP_FULL_MASK, lv > 0 && lv <= 16);
+            while (tiny) {
+                const int k0 = __ffs(tiny) - 1;
+                tiny &= tiny - 1;
+                const int k1 = tiny ? __ffs(tiny) - 1 : -1;
+                tiny &= tiny - 1;                       // 0 & anything stays 0
+                const int k = tile == 0 ? k0 : k1;
+                const int klv = __shfl_sync(RLAP_FULL_MASK, lv, k & 31);
+                const long long koff = __shfl_sync(RLAP_FULL_MASK, off, k & 31);
+                uint64_t a = (k >= 0 && tl < klv) ? P.raw[koff + tl] : RLAP_PAD_A;
+                a = T::sort_u64(a);
+                unsigned long long q;
+                int shift, mult;
+                const unsigned hmask = T::merge_sorted(a, q, shift, false, mult);
+                if (k >= 0 && ((hmask >> tl) & 1u)) P.raw[koff + __popc(hmask & tlt)] = a;
+                if (k >= 0 && tl == 0) P.outcnt[base + k] = __popc(hmask);
+            }
+        }
+        // 17..32 entries: one vertex at a time, all 32 lanes on its (contiguous) segment
+        unsigned small = __ballot_sync(RLAP_FULL_MASK, lv > 16 && lv <= 32);
         uint64_t a_next = RLAP_PAD_A;
         if (small) {
             int k = __ffs(small) - 1;
@@ -494,7 +521,7 @@ cudaError_t launch_emit_count(const SchurParams& P, long long* total_dev, cudaSt
         if (bx < 1) bx = 1;
         if (bx > 148 * 16) bx = 148 * 16;
         k_emit_base<<<(unsigned)bx, 256, 0, stream>>>(P);
-        long long work = P.pool_cap;
+        long long work = P.pool_cap / 2;
         bx = (work + 256 * 4 - 1) / (256 * 4);
         if (bx < 1) bx = 1;
         if (bx > 148 * 8) bx = 148 * 8;

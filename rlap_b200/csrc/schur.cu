@@ -124,18 +124,6 @@ __device__ int star_gather(const SchurParams& P, int view, int v, StarBuf sb, Ct
     return cnt;
 }
 
-template <bool LIVE>
-__device__ __forceinline__ void push_entry(const SchurParams& P, size_t vb, int4* pool, int owner, int nbr, float w,
-                                           int slot) {
-    int4 en;
-    en.x = nbr;
-    en.y = __float_as_int(w);
-    en.z = atomicExch(P.head + vb + owner, slot);
-    en.w = owner;
-    pool[slot] = en;
-    if (LIVE) atomicAdd(P.live + vb + owner, 1);
-}
-
 // degree / coarsen: appends to the next round's low list through a small per-warp shared buffer, so that the list
 // tail is bumped once per few dozen entries. Every member is warp-collective.
 constexpr int LOWBUF = 64;
