@@ -214,27 +214,45 @@ def run_ours(args):
     launches = {"n": 0}
     stats_acc = []
 
+    step_wall = []
+
     def step_device(step):
+        step_wall.append(time.perf_counter())
         g = ops.prepare(ei_dev, None, N_NODES)
         out, vp, st = ops.schur_views(g, t, O_V, O_N, num_views=V, seed=1234 + step, view_base=rank * V, dtype=None,
                                       return_stats=True)
         stats_acc.append(st)
-        # ingest: 12 kernel launches; views: setup, eliminate, prep, base, scatter, sort_warp, 4 x sort_mid, sort_block,
-        # sort_big, 2 x 3 scan, export, copy
-        launches["n"] += 12 + 20
+        # ingest: 12 kernel launches; views: setup, k_eliminate once per view group (min(V, 32) concurrent cooperative
+        # launches) + combine, prep, base, scatter, sort_warp, 4 x sort_mid, sort_block, sort_big, 2 x 3 scan, export, copy
+        groups = V // ((V + 31) // 32)
+        launches["n"] += 12 + 19 + groups + (1 if groups > 1 else 0)
         return out, vp
 
     # e2e: what a training loop that prefetches views does. Pinned host edge_index in, packed rows out to pinned
     # host buffers; the device->host copy of step i runs on a copy stream while step i+1 computes (two buffer
-    # sets). Every step's H2D and D2H are inside the timed region.
+    # sets). Every step's H2D and D2H are inside the timed region; at the end the host holds (row, col, w) of every
+    # view. The link is the bottleneck (26 MB per view). Shipping the column pointers instead of `col`
+    # (schur_views(colptr=True) + expand_cols) was measured here too: the D2H drops to 18 MB per view, but rebuilding
+    # col with 8-14 host threads competes with the DMA for this host's memory bandwidth and the step got slower
+    # (32 / 29 ms against 30 ms), so the plain rows are what is timed.
+    from concurrent.futures import ThreadPoolExecutor
     copy_stream = torch.cuda.Stream(device=dev)
     host_bufs = [dict(), dict()]
     pending = [None, None]
+    pool = ThreadPoolExecutor(max_workers=2)
+    d2h_bytes = {"n": 0}
+
+    def finish(done, total, keepalive):
+        # the device tensors stay referenced until their copies are done (no record_stream: the caching allocator
+        # would hold their blocks back behind cross-stream events and fall back to cudaMalloc, which synchronises)
+        done.synchronize()
+        del keepalive
+        return total
 
     def step_e2e(step):
         slot = step & 1
         if pending[slot] is not None:          # the buffers of this slot are still being filled by step - 2
-            pending[slot][0].synchronize()
+            pending[slot].result()
             pending[slot] = None
         d = ei_pinned.to(dev, non_blocking=True)
         g = ops.prepare(d, None, N_NODES)
@@ -253,17 +271,16 @@ def run_ours(args):
             hb["row"][:total].copy_(row, non_blocking=True)
             hb["col"][:total].copy_(col, non_blocking=True)
             hb["w"][:total].copy_(w, non_blocking=True)
-            for x in (row, col, w):
-                x.record_stream(copy_stream)
             done = torch.cuda.Event()
             done.record()
-        pending[slot] = (done, total)
+        d2h_bytes["n"] = total * 12
+        pending[slot] = pool.submit(finish, done, total, (row, col, w, g, d))
         return total
 
     def drain_e2e():
         for slot in (0, 1):
             if pending[slot] is not None:
-                pending[slot][0].synchronize()
+                pending[slot].result()
                 pending[slot] = None
 
     def barrier():
@@ -272,14 +289,14 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def timed(fn, steps, warmup):
+        res = None
         for s in range(warmup):
-            fn(s)
+            res = fn(s)       # same allocation pattern as the timed loop: the previous result stays alive during a step
         if fn is step_e2e:
             drain_e2e()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        res = None
         for s in range(steps):
             res = fn(warmup + s)
         if fn is step_e2e:
@@ -299,6 +316,11 @@ def run_ours(args):
     launches["n"] = 0
     ms_total, _ = timed(step_device, args.steps, args.warmup)
     timed_stats = stats_acc[args.warmup:]
+    if os.environ.get("BENCH_DEBUG"):
+        print("step starts (ms since first):", [round((x - step_wall[0]) * 1e3, 1) for x in step_wall], file=sys.stderr)
+        print("reserved MB", torch.cuda.memory_reserved() >> 20, "allocated MB", torch.cuda.memory_allocated() >> 20,
+              "num_alloc_retries", torch.cuda.memory_stats().get("num_alloc_retries"),
+              "segments", torch.cuda.memory_stats().get("segment.all.allocated"), file=sys.stderr)
     n_launch = launches["n"] * args.steps // (args.steps + args.warmup)
     clocks = sampler.stop()
     ms_e2e, total_rows = timed(step_e2e, args.steps, max(args.warmup, 1))
@@ -341,12 +363,16 @@ def run_ours(args):
         "edges_per_sec": value * E,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(ei_pinned.numel() * 8),
-                "d2h_bytes_per_step": int(total_rows * 12), "ms_per_step": ms_e2e / args.steps,
+                "d2h_bytes_per_step": int(d2h_bytes["n"]), "ms_per_step": ms_e2e / args.steps,
                 "api": "ops.prepare + ops.schur_views from pinned host edge_index; packed rows copied back to pinned host on a copy stream, overlapping the next step (2 buffer sets)"},
         "gpu_launches": int(n_launch),
         "roofline": {"bound": "hbm", "kernel": "k_eliminate", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": elim_us / 1e3,
+                     "launches_per_step": V // ((V + 31) // 32),
+                     "note": "k_eliminate runs as min(V, 32) concurrent cooperative launches (view groups, one grid "
+                             "barrier each); kernel_ms is the CUDA-event time from the first launch to the join of all "
+                             "of them and the bytes are those of all views of the step",
                      "kernel_share_of_step": elim_us / 1e3 / ms_step,
                      "emit_count_ms": count_us / 1e3,
                      "path": {"algorithmic_bytes_per_step": path_bytes, "achieved": path_gbs, "frac": path_gbs / peak}},

@@ -101,11 +101,25 @@ int rlap_schur_eliminate(int64_t n, int64_t nnz, const int32_t* csr_ptr, const i
  * (row = neighbour, col = surviving vertex, weight), both directions present, original node ids.
  * Either the packed device buffers (out_row/out_col int32, out_w float32) or out_f64 (device
  * double[rows,3], the reference's [E',3] float64 layout, py_api_binder.cc:33-51) or both may be
- * given; pass NULL for the ones not wanted. Must follow rlap_schur_eliminate on the same workspace.
+ * given; pass NULL for the ones not wanted (out_col alone may be NULL too: see rlap_schur_colptr).
+ * Must follow rlap_schur_eliminate on the same workspace.
  * Does not synchronise. */
 int rlap_schur_emit(int64_t n, int64_t nnz, const int32_t* csr_ptr, const int32_t* csr_col, const float* csr_w,
                     int64_t n_views, void* workspace, size_t workspace_bytes, int32_t* out_row, int32_t* out_col,
                     float* out_w, double* out_f64, void* stream);
+
+/* ---- column-pointer output (for consumers behind a PCIe link) -------------------------------------
+ * The rows of a view are sorted by (col, row), so `col` is implied by the number of rows per column.
+ * rlap_schur_emit with out_col = NULL writes rows and weights only; rlap_schur_colptr writes
+ * colptr[view * (n + 1) + v] = number of rows of `view` whose column is < v (device int32[n_views * (n + 1)],
+ * colptr[view * (n + 1) + n] = rows of the view): 4 (n + 1) bytes per view instead of 4 bytes per row.
+ * rlap_expand_cols_host rebuilds col (HOST int32[rows], views back to back at view_ptr[view], HOST int64[n_views + 1])
+ * from a HOST copy of colptr with n_threads host threads. No reference counterpart: the reference never
+ * leaves the host (py_api_binder.cc:54-69). */
+int rlap_schur_colptr(int64_t n, int64_t nnz, int64_t n_views, void* workspace, size_t workspace_bytes,
+                      int32_t* colptr, void* stream);
+int rlap_expand_cols_host(const int32_t* colptr, int64_t n_views, int64_t n, const int64_t* view_ptr, int32_t* out_col,
+                          int n_threads);
 
 /* ---- host-buffer entry point: the exact shape of approximate_cholesky_cpu (py_api_binder.cc:54-69)
  * edge_info: HOST row-major double[e,3] (row, col, weight) as rlap/ops.py:47 packs it. Allocates

@@ -18,7 +18,7 @@ FLAG_NO_VALIDATE = 4
 EXPORTS = [
     "rlap_status_string", "rlap_last_cuda_error", "rlap_version", "rlap_ingest_workspace_bytes", "rlap_ingest",
     "rlap_schur_workspace_bytes", "rlap_schur_eliminate", "rlap_schur_emit", "rlap_approximate_cholesky_host",
-    "rlap_free_host",
+    "rlap_free_host", "rlap_schur_colptr", "rlap_expand_cols_host",
 ]
 
 
@@ -55,6 +55,8 @@ def lib():
     L.rlap_approximate_cholesky_host.argtypes = [P, i64, i64, i64, ctypes.c_char_p, ctypes.c_char_p, u64,
                                                  ctypes.POINTER(ctypes.POINTER(ctypes.c_double)),
                                                  ctypes.POINTER(i64)]
+    L.rlap_schur_colptr.argtypes = [i64, i64, i64, P, sz, P, P]
+    L.rlap_expand_cols_host.argtypes = [P, i64, i64, P, P, ctypes.c_int]
     L.rlap_free_host.argtypes = [P]
     L.rlap_free_host.restype = None
     for name in EXPORTS:

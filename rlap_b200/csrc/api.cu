@@ -7,6 +7,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -21,6 +22,7 @@ cudaError_t launch_setup_graphs(int n, int G, const int* gptr, const long long* 
                                 cudaStream_t stream);
 cudaError_t eliminate_grid(int* blocks_out);
 cudaError_t launch_eliminate(const SchurParams& P, cudaStream_t stream, int blocks_req);
+cudaError_t launch_emit_colptr(const SchurParams& P, int* colptr, cudaStream_t stream);
 cudaError_t launch_combine_groups(int K, const int* gctr, const unsigned long long* gstats, int* ctr,
                                   unsigned long long* stats, cudaStream_t stream);
 cudaError_t launch_emit_count(const SchurParams& P, long long* total_dev, cudaStream_t stream);
@@ -355,11 +357,13 @@ int rlap_schur_eliminate(int64_t n, int64_t nnz, const int32_t* csr_ptr, const i
     P.k1 = (uint32_t)(seed >> 32);
     P.view_base = (uint32_t)view_base;
     {
-        std::vector<int> gp((size_t)n_graphs + 1);
+        // the converted graph pointers live until the next call of this thread; this call synchronises the stream
+        // before it returns, so no extra synchronisation (which would drain the caller's queued work) is needed here
+        static thread_local std::vector<int> gp;
+        gp.resize((size_t)n_graphs + 1);
         for (int64_t g = 0; g <= n_graphs; g++) gp[(size_t)g] = (int)graph_ptr[g];
         CK(cudaMemcpyAsync(L.gptr_dev, gp.data(), sizeof(int) * gp.size(), cudaMemcpyHostToDevice, stream));
         CK(cudaMemcpyAsync(L.nrem_dev, num_remove, sizeof(long long) * (size_t)n_graphs, cudaMemcpyHostToDevice, stream));
-        CK(cudaStreamSynchronize(stream));  // gp is a local
     }
     CK(cudaMemsetAsync(P.ctr, 0, sizeof(int) * CTR_COUNT, stream));
     CK(cudaMemsetAsync(P.stats, 0, sizeof(unsigned long long) * ST_COUNT, stream));
@@ -498,9 +502,64 @@ int rlap_schur_emit(int64_t n, int64_t nnz, const int32_t* csr_ptr, const int32_
     }
     if (L.P.n != n || L.P.nnz != nnz || L.V != n_views || workspace_bytes < L.bytes) return RLAP_ERR_INVALID_ARG;
     if (L.P.ptr != csr_ptr || L.P.col != csr_col || L.P.w != csr_w) return RLAP_ERR_INVALID_ARG;
-    if ((out_row || out_col || out_w) && !(out_row && out_col && out_w)) return RLAP_ERR_INVALID_ARG;
+    if ((out_row || out_col || out_w) && !(out_row && out_w)) return RLAP_ERR_INVALID_ARG;   // out_col alone may be NULL
     if (!out_row && !out_f64) return RLAP_ERR_INVALID_ARG;
     CK(launch_emit_write(L.P, out_row, out_col, out_w, out_f64, stream));
+    return RLAP_OK;
+}
+
+int rlap_schur_colptr(int64_t n, int64_t nnz, int64_t n_views, void* workspace, size_t workspace_bytes,
+                      int32_t* colptr, void* stream_v) {
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    SchurLayout L;
+    {
+        std::lock_guard<std::mutex> lk(g_layout_mutex);
+        auto it = g_layouts.find(workspace);
+        if (it == g_layouts.end()) return RLAP_ERR_INVALID_ARG;
+        L = it->second;
+    }
+    if (L.P.n != n || L.P.nnz != nnz || L.V != n_views || workspace_bytes < L.bytes || !colptr) return RLAP_ERR_INVALID_ARG;
+    CK(launch_emit_colptr(L.P, colptr, stream));
+    return RLAP_OK;
+}
+
+// Host side of the column-pointer output: rebuilds the `col` array of the packed rows from the per-view column
+// pointers with n_threads threads (a fill at memory speed; it replaces a third of the device-to-host traffic).
+int rlap_expand_cols_host(const int32_t* colptr, int64_t n_views, int64_t n, const int64_t* view_ptr, int32_t* out_col,
+                          int n_threads) {
+    if (!colptr || !view_ptr || !out_col || n_views < 0 || n < 1) return RLAP_ERR_INVALID_ARG;
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > 64) n_threads = 64;
+    const long long total_rows = view_ptr[n_views];
+    auto work = [&](int t) {
+        // thread t fills an equal share [r0, r1) of the rows: locate the view and the column of r0, then run forward
+        long long r0 = total_rows * t / n_threads;
+        const long long r1 = total_rows * (t + 1) / n_threads;
+        if (r0 >= r1) return;
+        long long lo = 0, hi = n_views;               // last view with view_ptr[view] <= r0
+        while (hi - lo > 1) { const long long mid = (lo + hi) >> 1; if (view_ptr[mid] <= r0) lo = mid; else hi = mid; }
+        long long view = lo;
+        while (r0 < r1) {
+            const int32_t* cp = colptr + view * (n + 1);
+            const long long vbase = view_ptr[view], vrows = view_ptr[view + 1] - vbase;
+            const long long rel0 = r0 - vbase, rel1 = (r1 - vbase < vrows) ? r1 - vbase : vrows;
+            long long a0 = 0, a1 = n;                 // last column with cp[col] <= rel0
+            while (a1 - a0 > 1) { const long long mid = (a0 + a1) >> 1; if (cp[mid] <= rel0) a0 = mid; else a1 = mid; }
+            int32_t* dst = out_col + vbase;
+            long long r = rel0;
+            for (long long v = a0; v < n && r < rel1; v++) {
+                const long long e = cp[v + 1] < rel1 ? cp[v + 1] : rel1;
+                for (; r < e; r++) dst[r] = (int32_t)v;
+            }
+            r0 = vbase + rel1;
+            view++;
+        }
+    };
+    if (n_threads == 1) { work(0); return RLAP_OK; }
+    std::vector<std::thread> th;
+    th.reserve((size_t)n_threads);
+    for (int t = 0; t < n_threads; t++) th.emplace_back(work, t);
+    for (auto& x : th) x.join();
     return RLAP_OK;
 }
 

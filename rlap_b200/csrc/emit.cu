@@ -485,7 +485,11 @@ __global__ void __launch_bounds__(256) k_emit_copy(SchurParams P, int* out_row, 
                 int v = v0 + lo;
                 while (v >= P.n) v -= P.n;   // the 32 vertices may straddle view boundaries (tiny graphs: several)
                 const long long w = dst0 + o;
-                if (out_row) { __stcs(out_row + w, (int)a_nbr(a)); __stcs(out_col + w, v); __stcs(out_w + w, a_w(a)); }
+                if (out_row) {
+                    __stcs(out_row + w, (int)a_nbr(a));
+                    if (out_col) __stcs(out_col + w, v);      // NULL: the caller rebuilds the columns from the column pointers
+                    __stcs(out_w + w, a_w(a));
+                }
                 if (out_f64) {
                     out_f64[w * 3 + 0] = (double)a_nbr(a);
                     out_f64[w * 3 + 1] = (double)v;
@@ -494,6 +498,15 @@ __global__ void __launch_bounds__(256) k_emit_copy(SchurParams P, int* out_row, 
             }
         }
     }
+}
+
+// column pointers of every view: colptr[view * (n + 1) + v] = rows of `view` that precede column v (v = n: all rows)
+__global__ void k_emit_colptr(SchurParams P, int* colptr) {
+    const long long VN1 = (long long)P.V * (P.n + 1);
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= VN1) return;
+    const long long view = t / (P.n + 1), v = t % (P.n + 1);
+    colptr[t] = (int)(P.outoff[view * P.n + v] - P.outoff[view * P.n]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -539,6 +552,12 @@ cudaError_t launch_emit_count(const SchurParams& P, long long* total_dev, cudaSt
     k_emit_sort_block<<<blocks, BLOCK_THREADS, smem, stream>>>(P);
     k_emit_sort_big<<<blocks / 2, BLOCK_THREADS, smem_big, stream>>>(P);
     return launch_exclusive_scan<long long>(P.outcnt, VN, P.outoff, P.blocksum, total_dev, stream);
+}
+
+cudaError_t launch_emit_colptr(const SchurParams& P, int* colptr, cudaStream_t stream) {
+    const long long VN1 = (long long)P.V * (P.n + 1);
+    k_emit_colptr<<<(unsigned)((VN1 + 255) / 256), 256, 0, stream>>>(P, colptr);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_emit_write(const SchurParams& P, int* out_row, int* out_col, float* out_w, double* out_f64,

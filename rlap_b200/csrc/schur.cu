@@ -5,7 +5,8 @@
 //   * the graph is an immutable coalesced CSR shared by all views; every view keeps only
 //     per-vertex state, a head pointer per vertex and an append-only pool of fill entries
 //     (lazy deletion: an entry dies when the vertex it points to is eliminated);
-//   * one persistent cooperative kernel runs ALL rounds of ALL views (grid.sync between phases);
+//   * one persistent cooperative kernel runs ALL rounds of the views of a view group (grid.sync between phases);
+//     the groups of a call run as concurrent launches (api.cu);
 //   * inside a round, vertices that are pairwise non-adjacent are eliminated concurrently, one warp
 //     (or one thread block for big stars) per vertex: gather -> fixed-point quantise -> bitonic sort
 //     by neighbour -> merge multi-edges -> o_n sort -> warp-shuffle prefix sums -> Philox-driven

@@ -109,13 +109,16 @@ def prepare(edge_index: Tensor, edge_weights: Optional[Tensor], num_nodes: int,
 
 def schur_views(graph: Graph, num_remove, o_v: str, o_n: str, num_views: int = 1, seed: Optional[int] = None,
                 view_base: int = 0, full_clique: bool = False, shared_order: bool = False, dtype=torch.float64,
-                pool_cap: int = 0, scratch_cap: int = 0, return_stats: bool = False):
+                pool_cap: int = 0, scratch_cap: int = 0, return_stats: bool = False, colptr: bool = False):
     """num_views independent randomized Schur-complement views of `graph`.
 
     Returns (edge_info, view_ptr): edge_info is [sum E'_v, 3] (row, col, weight) of `dtype`
     (float64 like the reference, or None for the packed form), views back to back, each sorted by
     (col, row); view_ptr is a host int64 tensor [num_views + 1]. With dtype=None returns
-    ((row int32, col int32, w float32), view_ptr). num_remove: int or one value per graph."""
+    ((row int32, col int32, w float32), view_ptr). num_remove: int or one value per graph.
+    colptr=True (with dtype=None): the `col` array is replaced by the per-view column pointers, an int32 tensor
+    [num_views, n + 1] (rows of a view are sorted by column, so col is implied; `expand_cols` rebuilds it on the
+    host) - a third less to move for consumers behind a PCIe link."""
     assert o_v in _O_V
     assert o_n in _O_N
     L = _native.lib()
@@ -154,12 +157,17 @@ def schur_views(graph: Graph, num_remove, o_v: str, o_n: str, num_views: int = 1
         view_ptr = torch.from_numpy(np.concatenate([[0], np.cumsum(rows)]).astype(np.int64))
         if dtype is None:
             orow = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
-            ocol = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
             ow = torch.empty(max(total, 1), dtype=torch.float32, device=dev)
+            if colptr:
+                ocp = torch.empty((V, graph.n + 1), dtype=torch.int32, device=dev)
+                _native.check(L.rlap_schur_colptr(graph.n, graph.nnz, V, ws.data_ptr(), wsb.value, ocp.data_ptr(), stream),
+                              "schur_colptr")
+            else:
+                ocol = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
             _native.check(L.rlap_schur_emit(graph.n, graph.nnz, graph.ptr.data_ptr(), graph.col.data_ptr(),
                                             graph.w.data_ptr(), V, ws.data_ptr(), wsb.value, orow.data_ptr(),
-                                            ocol.data_ptr(), ow.data_ptr(), 0, stream), "schur_emit")
-            out = (orow[:total], ocol[:total], ow[:total])
+                                            0 if colptr else ocol.data_ptr(), ow.data_ptr(), 0, stream), "schur_emit")
+            out = (orow[:total], ocp if colptr else ocol[:total], ow[:total])
         else:
             o64 = torch.empty((max(total, 1), 3), dtype=torch.float64, device=dev)
             _native.check(L.rlap_schur_emit(graph.n, graph.nnz, graph.ptr.data_ptr(), graph.col.data_ptr(),
@@ -174,6 +182,21 @@ def schur_views(graph: Graph, num_remove, o_v: str, o_n: str, num_views: int = 1
                  "t_elim_block_us", "check_mismatches"]
         return out, view_ptr, dict(zip(names, (int(x) for x in stats)))
     return out, view_ptr
+
+
+def expand_cols(colptr_host: Tensor, view_ptr: Tensor, out: Optional[Tensor] = None, threads: int = 8) -> Tensor:
+    """host side of schur_views(colptr=True): the int32 `col` array of the packed rows, rebuilt from a HOST copy of
+    the column pointers [num_views, n + 1] and view_ptr with `threads` host threads (C, no Python loop)."""
+    assert not colptr_host.is_cuda and colptr_host.dtype == torch.int32 and colptr_host.is_contiguous()
+    V, n1 = colptr_host.shape
+    vp = view_ptr.to(torch.int64).contiguous()
+    total = int(vp[-1])
+    if out is None:
+        out = torch.empty(max(total, 1), dtype=torch.int32)
+    assert out.dtype == torch.int32 and out.numel() >= total and out.is_contiguous()
+    _native.check(_native.lib().rlap_expand_cols_host(colptr_host.data_ptr(), V, n1 - 1, vp.data_ptr(), out.data_ptr(),
+                                                      int(threads)), "expand_cols_host")
+    return out[:total]
 
 
 def approximate_cholesky_batched(edge_index: Tensor, edge_weights: Optional[Tensor], num_nodes: int, num_remove,

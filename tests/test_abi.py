@@ -74,3 +74,23 @@ def test_product_does_not_touch_the_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "from oracle" not in txt and "import oracle" not in txt and "oracle/" not in txt.replace(
                     "oracle/rlap_oracle.cc (keyed mode)", ""), os.path.join(dirpath, f)
+
+
+def test_expand_cols_host():
+    """the host half of the column-pointer output needs no GPU: col rebuilt from column pointers, any thread count,
+    empty views and empty columns included"""
+    import numpy as np
+    import torch
+    from rlap_b200 import ops
+    rng = np.random.default_rng(0)
+    V, n = 5, 1000
+    cnt = rng.integers(0, 6, size=(V, n))
+    cnt[:, :50] += rng.integers(0, 400, size=(V, 50))
+    cnt[2] = 0
+    cp = np.zeros((V, n + 1), dtype=np.int32)
+    cp[:, 1:] = np.cumsum(cnt, axis=1)
+    vp = np.concatenate([[0], np.cumsum(cp[:, -1])]).astype(np.int64)
+    ref = np.concatenate([np.repeat(np.arange(n, dtype=np.int32), cnt[v]) for v in range(V)])
+    for threads in (1, 3, 8, 64):
+        out = ops.expand_cols(torch.from_numpy(cp), torch.from_numpy(vp), threads=threads).numpy()
+        assert np.array_equal(out, ref), threads

@@ -251,3 +251,17 @@ def test_many_desynchronised_views_match_oracle(oracle_port, o_v):
         assert e - s == r0.shape[0], (v, e - s, r0.shape[0])
         assert np.array_equal(row[s:e], r0) and np.array_equal(col[s:e], c0), v
         assert np.array_equal(wt[s:e].view(np.uint32), w0.view(np.uint32)), v
+
+
+def test_column_pointer_output_matches_packed_rows():
+    """schur_views(colptr=True) + expand_cols == the col array of the packed rows (rows and weights unchanged)"""
+    import rlap_b200
+    from rlap_b200 import graphs, ops
+    for name, ei, n, gptr, t in util.small_cases():
+        g = _gpu_graph(ei, None, n, gptr)
+        (row, col, wt), vp = rlap_b200.schur_views(g, t, "degree", "asc", num_views=5, seed=3, dtype=None)
+        (row2, cp, wt2), vp2 = rlap_b200.schur_views(g, t, "degree", "asc", num_views=5, seed=3, dtype=None, colptr=True)
+        assert torch.equal(vp, vp2) and torch.equal(row, row2) and torch.equal(wt, wt2), name
+        assert cp.shape == (5, n + 1) and cp.dtype == torch.int32
+        col2 = ops.expand_cols(cp.cpu(), vp2, threads=4)
+        assert torch.equal(col.cpu()[: int(vp[-1])], col2), name
