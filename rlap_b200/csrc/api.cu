@@ -405,6 +405,7 @@ int rlap_schur_eliminate(int64_t n, int64_t nnz, const int32_t* csr_ptr, const i
                 Q.V = (int)Vg;
                 Q.view_base = P.view_base + (uint32_t)v0;
                 Q.state += o; Q.live += o; Q.head += o; Q.rank += o; Q.blk += o; Q.candround += o;
+                Q.outoff += o;                                         // phase A's (round, key) snapshots live here
                 Q.pool += (size_t)v0 * (size_t)P.pool_cap;
                 Q.pool_cursor += v0;
                 Q.rem += og; Q.lvl += og; Q.cntI += og; Q.ovfseg += og; Q.thresh += og;

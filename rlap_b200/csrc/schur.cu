@@ -728,6 +728,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
             P.state[idx] = (__ldg(P.ptr + v + 1) == __ldg(P.ptr + v)) ? 4 : 1;
             P.candround[idx] = -1;
             P.rank[idx] = -1;   // degree / coarsen: round stamp of the low list
+            P.outoff[idx] = 0;  // (round, key) snapshot of phase A (rounds are stored + 1: 0 = never visited)
         }
     }
     if (!random_order) {
@@ -854,6 +855,10 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
         // list of a segment has an entry in play the bucket is taken from the list alone.
         constexpr int SEG_SM = 1024, WBUF = 320;
         const int INF = 0x7fffffff;
+        // (round, key) snapshots written by phase A, read by the bucket test of phase B; the emission's row offsets
+        // are not needed before the elimination is over
+        unsigned long long* mark = (unsigned long long*)P.outoff;
+        auto mark_of = [](int round, int key) { return ((unsigned long long)(unsigned)(round + 1) << 32) | (unsigned)key; };
         int* mkl = P.minkey;          // minimum over the low list
         int* mks = P.minkey + VG;     // minimum over a full scan
         const bool bsm = VG <= (long long)SEG_SM;
@@ -889,6 +894,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
                             seg = (int)(idx / un) * P.G + graph_of(P, (int)(idx % un));
                             key = (st == 4) ? 0 : max(ldcg_i32(P.live + idx), 1);
                             valid = ldcg_i32(P.rem + seg) > 0 && key <= ldcg_i32(P.lvl + seg);
+                            if (valid) mark[idx] = mark_of(rounds, key);
                         }
                     }
                     const unsigned vm = __ballot_sync(RLAP_FULL_MASK, valid);
@@ -954,6 +960,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
                 for (unsigned base = (unsigned)(tid - lane); base < total; base += 4u * (unsigned)nthr) {
                     uint8_t st4[4];
                     int lv4[4], sg4[4];
+                    unsigned ix4[4];
                     bool nd4[4];
 #pragma unroll
                     for (int q4 = 0; q4 < 4; q4++) {
@@ -966,6 +973,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
                         if (e < total) {
                             const int view = bsm ? sviews[sv] : (int)sv;
                             const unsigned idx = (unsigned)view * un + (unsigned)v;
+                            ix4[q4] = idx;
                             sg4[q4] = view * P.G + graph_of(P, v);
                             nd4[q4] = bsm ? (sneed[sg4[q4]] != 0)
                                           : (ldcg_i32(P.rem + sg4[q4]) > 0 && ldcg_i32(mkl + sg4[q4]) == INF);
@@ -980,6 +988,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
                         const bool valid = nd4[q4] && st4[q4] != 2;
                         const int seg = sg4[q4];
                         const int key = valid ? ((st4[q4] == 4) ? 0 : max(lv4[q4], 1)) : INF;
+                        if (valid) mark[ix4[q4]] = mark_of(rounds, key);
                         const unsigned vm = __ballot_sync(RLAP_FULL_MASK, valid);
                         if (vm == 0) continue;
                         any = true;
@@ -1066,35 +1075,31 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
                 __syncwarp();
                 wfill = 0;
             };
-            // bucket member v of `view` (key m): true if no alive neighbour of higher id has key m
+            // bucket member v of `view` (key m): true if no alive neighbour of higher id has key m. Phase A left the
+            // (round, key) snapshot of every vertex it visited in `mark`: all alive vertices of a rescanning segment,
+            // all vertices in play otherwise, i.e. every alive vertex whose key can equal m. One 8-byte load per
+            // neighbour answers "alive bucket member?" (an eliminated or unvisited neighbour carries an older round).
             auto member_free = [&](unsigned idx, int view, int v, int m) -> bool {
                 const size_t vb = (size_t)view * P.n;
+                const unsigned long long want = mark_of(rounds, m);
                 bool ok = true;
-                // base neighbours, four at a time: ids first, then states and live counters together
+                // base neighbours, four at a time: ids first, then their snapshots together
                 const int pb = __ldg(P.ptr + v), pe = __ldg(P.ptr + v + 1);
                 for (int p = pb; p < pe && ok; p += 4) {
                     int u4[4];
 #pragma unroll
                     for (int k = 0; k < 4; k++) u4[k] = (p + k < pe) ? __ldg(P.col + p + k) : -1;
-                    uint8_t s4[4];
-                    int l4[4];
+                    unsigned long long k4[4];
 #pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        s4[k] = 2; l4[k] = 0;
-                        if (u4[k] > v) { s4[k] = ldcg_u8(P.state + vb + u4[k]); l4[k] = ldcg_i32(P.live + vb + u4[k]); }
-                    }
+                    for (int k = 0; k < 4; k++) k4[k] = (u4[k] > v) ? __ldcg(mark + vb + u4[k]) : 0ull;
 #pragma unroll
                     for (int k = 0; k < 4; k++)
-                        if (u4[k] > v && s4[k] != 2 && max(l4[k], 1) == m) ok = false;
+                        if (u4[k] > v && k4[k] == want) ok = false;
                 }
                 const int4* pool = P.pool + (size_t)view * (size_t)P.pool_cap;
                 for (int p = ldcg_i32(P.head + idx); p >= 0 && ok;) {
                     int4 en = __ldcg(pool + p);
-                    if (en.x > v) {
-                        uint8_t su = ldcg_u8(P.state + vb + en.x);
-                        int lu = ldcg_i32(P.live + vb + en.x);
-                        if (su != 2 && max(lu, 1) == m) ok = false;
-                    }
+                    if (en.x > v && __ldcg(mark + vb + en.x) == want) ok = false;
                     p = en.z;
                 }
                 return ok;
