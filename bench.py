@@ -347,7 +347,7 @@ def run_ours(args):
     # measured DRAM traffic of the same kernel from the committed ncu --set full capture (same workload and V)
     traffic = None
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01b_k_eliminate_traffic.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01c_k_eliminate_traffic.json")))
         if int(tj.get("views_per_launch", 0)) == V:
             traffic = float(tj["traffic_bytes_per_launch"])
     except Exception:
