@@ -262,8 +262,7 @@ static SchurLayout schur_layout(long long n, long long nnz, long long G, long lo
     L.teff_dev = c.take<int>((size_t)G);
     L.gid_dev = c.take<int>(G > 1 ? (size_t)n : 1);
     P.state = c.take<uint8_t>(VN);
-    P.live = c.take<int>(VN);
-    P.head = c.take<int>(VN);
+    P.lh = c.take<int>(2 * VN);
     P.rank = c.take<int>(VN);
     P.blk = c.take<int>(VN);
     P.candround = c.take<int>(VN);
@@ -404,7 +403,7 @@ int rlap_schur_eliminate(int64_t n, int64_t nnz, const int32_t* csr_ptr, const i
                 const size_t o = (size_t)v0 * (size_t)n, og = (size_t)v0 * (size_t)G;
                 Q.V = (int)Vg;
                 Q.view_base = P.view_base + (uint32_t)v0;
-                Q.state += o; Q.live += o; Q.head += o; Q.rank += o; Q.blk += o; Q.candround += o;
+                Q.state += o; Q.lh += 2 * o; Q.rank += o; Q.blk += o; Q.candround += o;
                 Q.outoff += o;                                         // phase A's (round, key) snapshots live here
                 Q.pool += (size_t)v0 * (size_t)P.pool_cap;
                 Q.pool_cursor += v0;

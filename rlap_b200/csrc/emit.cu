@@ -32,7 +32,7 @@ __global__ void k_emit_prep(SchurParams P) {
     long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= VN) return;
     if (run_failed(P)) { rawcnt_of(P)[idx] = 0; cursor_of(P)[idx] = 0; P.outcnt[idx] = 0; return; }
-    int c = (P.state[idx] != 2) ? P.live[idx] : 0;
+    int c = (P.state[idx] != 2) ? *live_p(P, idx) : 0;
     rawcnt_of(P)[idx] = c;
     cursor_of(P)[idx] = 0;
 }

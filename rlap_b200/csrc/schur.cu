@@ -32,10 +32,10 @@ __device__ __forceinline__ int graph_of(const SchurParams& P, int v) { return P.
 // state byte: 0 kept (o_v = random, not eligible), 1 pending, 2 eliminated, 4 pending and isolated from the start
 __device__ __forceinline__ int key_eff(const SchurParams& P, size_t idx, uint8_t st) {
     if (st == 4) return 0;
-    return max(ldcg_i32(P.live + idx), 1);
+    return max(ldcg_i32(live_p(P, idx)), 1);
 }
 __device__ __forceinline__ int key_nbr(const SchurParams& P, size_t vb, int u) {  // u has an edge: deg0 > 0
-    return max(ldcg_i32(P.live + vb + u), 1);
+    return max(ldcg_i32(live_p(P, vb + u)), 1);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -67,7 +67,7 @@ __device__ int star_gather(const SchurParams& P, int view, int v, StarBuf sb, Ct
         float w = 0.f;
         if (ok) {
             u = __ldg(P.col + p);
-            ok = ldcg_u8(st + u) != 2;
+            ok = ldcg_i32(live_p(P, vb + u)) >= 0;   // an eliminated vertex carries RLAP_LIVE_DEAD
         }
         if (ok) w = __ldg(P.w + p);
         unsigned m = __ballot_sync(RLAP_FULL_MASK, ok);
@@ -89,7 +89,7 @@ __device__ int star_gather(const SchurParams& P, int view, int v, StarBuf sb, Ct
     // appended fill entries: a linked list, walked by one warp; 32 hops are collected before the
     // (dependent) state lookups so that those run in parallel
     if (!CTA || (threadIdx.x >> 5) == 0) {
-        int p = ldcg_i32(P.head + vb + v);
+        int p = ldcg_i32(head_p(P, vb + v));
         while (p >= 0) {
             int4 mine = make_int4(0, 0, 0, 0);
             bool have = false;
@@ -98,7 +98,7 @@ __device__ int star_gather(const SchurParams& P, int view, int v, StarBuf sb, Ct
                 if (lane == k) { mine = en; have = true; }
                 p = en.z;
             }
-            bool ok = have && (ldcg_u8(st + mine.x) != 2);
+            bool ok = have && (ldcg_i32(live_p(P, vb + mine.x)) >= 0);
             unsigned m = __ballot_sync(RLAP_FULL_MASK, ok);
             int base;
             if (CTA) {
@@ -188,8 +188,8 @@ __device__ __forceinline__ bool push_fill(const SchurParams& P, size_t vb, int4*
     }
     {   // both list heads are exchanged before either entry is written: the two round trips overlap
         const int s0 = (int)slot, s1 = (int)slot + 1;
-        const int n0 = atomicExch(P.head + vb + j, s0);
-        const int n1 = atomicExch(P.head + vb + k, s1);
+        const int n0 = atomicExch(head_p(P, vb + j), s0);
+        const int n1 = atomicExch(head_p(P, vb + k), s1);
         if (pend) {
             pend->e0 = make_int4(k, __float_as_int(w), n0, j);
             pend->e1 = make_int4(j, __float_as_int(w), n1, k);
@@ -198,7 +198,7 @@ __device__ __forceinline__ bool push_fill(const SchurParams& P, size_t vb, int4*
             pool[s0] = make_int4(k, __float_as_int(w), n0, j);
             pool[s1] = make_int4(j, __float_as_int(w), n1, k);
         }
-        if (LIVE) { atomicAdd(P.live + vb + j, 1); atomicAdd(P.live + vb + k, 1); }
+        if (LIVE) { atomicAdd(live_p(P, vb + j), 1); atomicAdd(live_p(P, vb + k), 1); }
     }
     if (P.o_v == 0) {
         if (ldcg_u8(P.state + vb + j) == 1 && ldcg_u8(P.state + vb + k) == 1) {
@@ -326,7 +326,7 @@ __device__ void eliminate_star(const SchurParams& P, const RoundCtx& rc, int vie
                 const uint64_t a = sb.A[i];
                 if (a != RLAP_PAD_A) {
                     u = (int)a_nbr(a);
-                    const int old = atomicSub(P.live + vb + u, 1);
+                    const int old = atomicSub(live_p(P, vb + u), 1);
                     cross = old > M && old - 1 <= M;
                     if (P.o_v == 0 && ldcg_u8(P.state + vb + u) == 1) {
                         int oldb = atomicSub(P.blk + vb + u, 1);
@@ -345,7 +345,7 @@ __device__ void eliminate_star(const SchurParams& P, const RoundCtx& rc, int vie
             ls.raw += (unsigned long long)lraw;
         }
     }
-    if (r == 0) P.state[vb + v] = 2;
+    if (r == 0) { P.state[vb + v] = 2; *live_p(P, vb + v) = RLAP_LIVE_DEAD; }
     g_sync<CTA>();
 }
 
@@ -373,7 +373,9 @@ __device__ void eliminate_star_tile(const SchurParams& P, const RoundCtx& rc, un
         else if (tl - nb < nfill) a = fills[tl - nb];
     }
     bool dead = false;
-    if (a != RLAP_PAD_A) dead = ldcg_u8(P.state + vb + a_nbr(a)) == 2;
+    // dead test on the neighbour's (live, head) record: the sector is the one its live counter and list head are
+    // updated in further down
+    if (a != RLAP_PAD_A) dead = ldcg_i32(live_p(P, vb + a_nbr(a))) < 0;
     // the previous star's pool entries: their `next` fields have arrived by now
     pend.flush(la);
     if (dead) a = RLAP_PAD_A;
@@ -392,7 +394,7 @@ __device__ void eliminate_star_tile(const SchurParams& P, const RoundCtx& rc, un
     // receives. The extra multiplicity goes now, the rest is netted per merged neighbour after sampling.
     bool cross0 = false;
     if (go && ((hmask >> tl) & 1u) && mult > 1) {
-        const int old = atomicSub(P.live + vb + rawnbr, mult - 1);
+        const int old = atomicSub(live_p(P, vb + rawnbr), mult - 1);
         cross0 = old > M && old - (mult - 1) <= M;
     }
     const bool live = (hmask >> tl) & 1u;
@@ -474,7 +476,7 @@ __device__ void eliminate_star_tile(const SchurParams& P, const RoundCtx& rc, un
             float w = __double2float_rn(__ddiv_rn(__dmul_rn((double)a_w(a), __ull2double_rn(rem)), __ull2double_rn(S)));
             if (push_fill<false>(P, vb, pool, (int)a_nbr(a), (int)a_nbr(ek), w, slot0 + 2LL * tl, &pend)) {
                 delta++;
-                atomicAdd(P.live + vb + (int)a_nbr(ek), 1);
+                atomicAdd(live_p(P, vb + (int)a_nbr(ek)), 1);
             }
         }
     }
@@ -485,7 +487,7 @@ __device__ void eliminate_star_tile(const SchurParams& P, const RoundCtx& rc, un
     // neighbours whose live counter crossed the segment's level downwards join the next round's low list; the test
     // on the value the atomic returns is left to the next flush of `pend`
     if (go && tl < L && delta != 0) {
-        const int old = atomicAdd(P.live + vb + (int)a_nbr(a), delta);
+        const int old = atomicAdd(live_p(P, vb + (int)a_nbr(a)), delta);
         if (delta < 0) { pend.lo_old = old; pend.lo_M = M; pend.lo_lim = M - delta; pend.lo_idx = (unsigned int)(vb + (size_t)a_nbr(a)); }
     }
     la.push(cross0, (unsigned int)(vb + (size_t)rawnbr));
@@ -503,6 +505,7 @@ __device__ void eliminate_star_tile(const SchurParams& P, const RoundCtx& rc, un
         ls.maxstar = max(ls.maxstar, L);
         ls.raw += (unsigned long long)lraw;
         P.state[vb + v] = 2;
+        *live_p(P, vb + v) = RLAP_LIVE_DEAD;
     }
     __syncwarp();
 }
@@ -556,31 +559,32 @@ __device__ void run_warp_items(const SchurParams& P, const RoundCtx& rc, uint64_
     uint64_t* fbuf = sb.A;   // 32 x FCAP staged fill entries; the shared-memory path reuses the area afterwards
     const int count = end - start;
     if (count <= 0) return;
-    // Every block owns a contiguous slice of the items; its warps fetch chunks of the slice from a shared-memory
-    // cursor, so a warp that drew expensive stars takes fewer chunks (a static stride left the phase waiting for the
-    // warps with one chunk more than the others). flags & 256: the static schedule, for comparison.
+    // All warps of the launch (a view group: ~150 warps) fetch chunks of the round's work list from one global cursor,
+    // with a guided size: 1 / (2 x warps) of what is left, at least 4 and at most 32 items. Blocks share their SMs
+    // with the blocks of other groups and run at different speeds; per-block slices left a third of the phase's warp
+    // time waiting for the slowest block (wait timers, profiles/README.md). A stale read of the cursor only changes a
+    // chunk size. flags & 256: static stride, for comparison.
     const bool dynamic = (P.flags & 256) == 0;
-    int chunk, c0, cstep, my_end;
-    if (dynamic) {
-        const long long nb = gridDim.x, bid = blockIdx.x;
-        const int bs = start + (int)((long long)count * bid / nb), be = start + (int)((long long)count * (bid + 1) / nb);
-        chunk = (be - bs + 3 * WARPS_PER_BLOCK - 1) / (3 * WARPS_PER_BLOCK);
-        chunk = (chunk + 3) & ~3;
-        if (chunk > 32) chunk = 32;
-        if (chunk < 4) chunk = 4;
-        if (threadIdx.x == 0) *next = bs;
-        __syncthreads();
-        my_end = be;
-        c0 = 0; cstep = 0;
-    } else {
+    int chunk = 32, c0 = 0, cstep = 0, chunk_now = 0;
+    const int my_end = end;
+    if (!dynamic) {
         chunk = (count + nw - 1) / nw;       // spread small rounds over all warps
         if (chunk > 32) chunk = 32;
-        c0 = start + gw * chunk; cstep = nw * chunk; my_end = end;
+        c0 = start + gw * chunk; cstep = nw * chunk;
     }
+    (void)next;
     for (;; c0 += cstep) {
         if (dynamic) {
-            if (lane == 0) c0 = atomicAdd(next, chunk);
+            if (lane == 0) {
+                const int left = count - ldcg_i32(P.ctr + rc.sslot);
+                int c = left / (2 * nw);
+                c = (c + 3) & ~3;
+                c = c < 4 ? 4 : (c > 32 ? 32 : c);
+                c0 = start + atomicAdd(P.ctr + rc.sslot, c);
+                chunk_now = c;
+            }
             c0 = __shfl_sync(RLAP_FULL_MASK, c0, 0);
+            chunk_now = __shfl_sync(RLAP_FULL_MASK, chunk_now, 0);
         }
         if (c0 >= my_end) break;
         const int end = my_end;
@@ -588,7 +592,7 @@ __device__ void run_warp_items(const SchurParams& P, const RoundCtx& rc, uint64_
         unsigned int idx = 0xffffffffu;
         int lv = -1, cls = -1, b = 0, nb = 0, nfill = 0, M = -1;
         __syncwarp();   // the previous chunk is done with the staging buffer
-        if (lane < chunk && it < end) {
+        if (lane < (dynamic ? chunk_now : chunk) && it < end) {
             idx = __ldcg(P.wl + it);
             const int view = (int)(idx / (unsigned)P.n), v = (int)(idx % (unsigned)P.n);
             bool skip = false;
@@ -598,14 +602,14 @@ __device__ void run_warp_items(const SchurParams& P, const RoundCtx& rc, uint64_
                 M = ldcg_i32(P.lvl + seg);
             }
             if (!skip) {
-                lv = ldcg_i32(P.live + idx);
+                lv = ldcg_i32(live_p(P, idx));
                 b = __ldg(P.ptr + v);
                 nb = __ldg(P.ptr + v + 1) - b;
                 if (lv <= CAP_WARP) {
                     // every lane walks the fill list of its own item (32 chains in flight) into the staging buffer;
                     // with the CSR bounds this gives the exact raw length, i.e. the tile width that holds the star
                     const int4* pool = P.pool + (size_t)view * (size_t)P.pool_cap;
-                    int p = ldcg_i32(P.head + idx);
+                    int p = ldcg_i32(head_p(P, idx));
                     while (p >= 0 && nfill < FCAP) {
                         const int4 en = __ldcg(pool + p);
                         fbuf[lane * FCAP + nfill] = pack_a((uint32_t)en.x, __int_as_float(en.y));
@@ -681,7 +685,7 @@ __device__ void run_block_items(const SchurParams& P, const RoundCtx& rc, uint64
     for (int it = start + (int)blockIdx.x; it < end; it += (int)gridDim.x) {
         unsigned int idx = __ldcg(P.dl + it);
         int view = (int)(idx / (unsigned)P.n), v = (int)(idx % (unsigned)P.n);
-        if (ldcg_i32(P.live + idx) <= CAP_CTA) eliminate_star<true>(P, rc, view, v, cta_buf(smem), cs, ls, la);
+        if (ldcg_i32(live_p(P, idx)) <= CAP_CTA) eliminate_star<true>(P, rc, view, v, cta_buf(smem), cs, ls, la);
         __syncthreads();
     }
     const int nslot = min(NSLOT, (int)gridDim.x);   // a view group may run on fewer blocks than there are slots
@@ -689,7 +693,7 @@ __device__ void run_block_items(const SchurParams& P, const RoundCtx& rc, uint64
         int j = 0;
         for (int it = start; it < end; it++) {
             unsigned int idx = __ldcg(P.dl + it);
-            if (ldcg_i32(P.live + idx) <= CAP_CTA) continue;
+            if (ldcg_i32(live_p(P, idx)) <= CAP_CTA) continue;
             if ((j++ % nslot) != (int)blockIdx.x) continue;
             int view = (int)(idx / (unsigned)P.n), v = (int)(idx % (unsigned)P.n);
             eliminate_star<true>(P, rc, view, v, scratch_buf(P), cs, ls, la);
@@ -713,8 +717,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
     // ---- init: per-vertex state (ordering kernel for o_v = random: keyed Feistel rank)
     for (long long idx = tid; idx < VN; idx += nthr) {
         int view = (int)(idx / P.n), v = (int)(idx % P.n);
-        P.live[idx] = __ldg(P.ptr + v + 1) - __ldg(P.ptr + v);
-        P.head[idx] = -1;
+        *live_p(P, idx) = __ldg(P.ptr + v + 1) - __ldg(P.ptr + v);
+        *head_p(P, idx) = -1;
         if (random_order) {
             int g = graph_of(P, v);
             int gb = __ldg(P.gptr + g), ng = __ldg(P.gptr + g + 1) - gb;
@@ -831,7 +835,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
             // items to consume were appended in the previous round
             int wl_end = wl_start + ldcg_i32(P.ctr + CTR_WCNT0 + (rounds + 2) % 3);
             if (wl_end == wl_start) break;
-            if (tid == 0) { P.ctr[CTR_WCNT0 + (rounds + 1) % 3] = 0; P.ctr[CTR_DCNT0 + (rounds + 1) % 3] = 0; }
+            if (tid == 0) { P.ctr[CTR_WCNT0 + (rounds + 1) % 3] = 0; P.ctr[CTR_DCNT0 + (rounds + 1) % 3] = 0; P.ctr[CTR_STEAL0 + (rounds + 1) % 3] = 0; }
+            rc.sslot = CTR_STEAL0 + rounds % 3;
             rc.wl_base = wl_end; rc.wslot = CTR_WCNT0 + rounds % 3;
             rc.dl_base = dl_start; rc.dslot = CTR_DCNT0 + rounds % 3;
             run_warp_items(P, rc, smem, &cs, &s_next, wl_start, wl_end, ls, la);
@@ -874,9 +879,11 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
             if (ldcg_i32(P.ctr + CTR_LOWOVF0 + par)) n_in = 0;   // entries were lost: every segment rescans
             rc.wl_base = wl_start; rc.wslot = CTR_WCNT0 + rounds % 3;
             rc.dl_base = dl_start; rc.dslot = CTR_DCNT0 + rounds % 3;
+            rc.sslot = CTR_STEAL0 + rounds % 3;
             if (tid == 0) {
                 P.ctr[CTR_ACTIVE0 + (par ^ 1)] = 0; P.ctr[CTR_OVF0 + (par ^ 1)] = 0;
                 P.ctr[CTR_WCNT0 + (rounds + 1) % 3] = 0; P.ctr[CTR_DCNT0 + (rounds + 1) % 3] = 0;
+                P.ctr[CTR_STEAL0 + (rounds + 1) % 3] = 0;
                 P.ctr[CTR_LOW0 + (par ^ 1)] = 0; P.ctr[CTR_LOWOVF0 + (par ^ 1)] = 0;
             }
             for (long long s = tid; s < VG; s += nthr) { P.cntI[s] = 0; P.ovfseg[s] = 0; }
@@ -892,7 +899,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
                         const uint8_t st = ldcg_u8(P.state + idx);
                         if (st != 2) {
                             seg = (int)(idx / un) * P.G + graph_of(P, (int)(idx % un));
-                            key = (st == 4) ? 0 : max(ldcg_i32(P.live + idx), 1);
+                            key = (st == 4) ? 0 : max(ldcg_i32(live_p(P, idx)), 1);
                             valid = ldcg_i32(P.rem + seg) > 0 && key <= ldcg_i32(P.lvl + seg);
                             if (valid) mark[idx] = mark_of(rounds, key);
                         }
@@ -979,7 +986,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
                                           : (ldcg_i32(P.rem + sg4[q4]) > 0 && ldcg_i32(mkl + sg4[q4]) == INF);
                             if (nd4[q4]) {
                                 st4[q4] = ldcg_u8(P.state + idx);
-                                lv4[q4] = ldcg_i32(P.live + idx);
+                                lv4[q4] = ldcg_i32(live_p(P, idx));
                             }
                         }
                     }
@@ -1097,7 +1104,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
                         if (u4[k] > v && k4[k] == want) ok = false;
                 }
                 const int4* pool = P.pool + (size_t)view * (size_t)P.pool_cap;
-                for (int p = ldcg_i32(P.head + idx); p >= 0 && ok;) {
+                for (int p = ldcg_i32(head_p(P, idx)); p >= 0 && ok;) {
                     int4 en = __ldcg(pool + p);
                     if (en.x > v && __ldcg(mark + vb + en.x) == want) ok = false;
                     p = en.z;
@@ -1136,7 +1143,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
                         int m, lv;
                         bool scan;
                         seg_round(seg, rm, m, scan, lv);
-                        const int key = (st == 4) ? 0 : max(ldcg_i32(P.live + idx), 1);
+                        const int key = (st == 4) ? 0 : max(ldcg_i32(live_p(P, idx)), 1);
                         // in play, and the first copy of this vertex on the list (P.rank holds the round stamp)
                         if (rm > 0 && !scan && key <= lv && atomicExch(P.rank + idx, rounds) != rounds) {
                             if (key == m && member_free(idx, view, v, m)) cand = true; else keep = true;
@@ -1176,7 +1183,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
                             seg_round(sg4[q4], rm4[q4], mk4[q4], scan, lvq);
                             if (scan && rm4[q4] > 0 && mk4[q4] != INF) {
                                 st4[q4] = ldcg_u8(P.state + idx);
-                                lv4[q4] = ldcg_i32(P.live + idx);
+                                lv4[q4] = ldcg_i32(live_p(P, idx));
                             } else {
                                 mk4[q4] = -1;
                             }

@@ -68,8 +68,10 @@ struct SchurParams {
     int V;
     // per view state, all indexed [view * n + v]
     uint8_t* state;    // 0 kept (not eligible), 1 pending, 2 eliminated
-    int* live;         // number of raw entries whose neighbour is not eliminated
-    int* head;         // head of the appended fill-entry list (pool index, -1 = empty)
+    int* lh;           // [V*n][2] interleaved: live = number of raw entries whose neighbour is not eliminated
+                       // (RLAP_LIVE_DEAD once the vertex itself is eliminated), head = head of the appended fill-entry
+                       // list (pool index, -1 = empty). One 8-byte record: the dead test of a neighbour, the update of
+                       // its live counter and the exchange of its list head touch the same 32-byte sector.
     int* rank;         // o_v = random: rank in the keyed permutation
     int* blk;          // o_v = random: pending lower-ranked eligible neighbours (raw multiplicity)
     int* candround;    // degree / coarsen: last round in which the vertex was selected
@@ -103,5 +105,9 @@ struct SchurParams {
     int scratch_cap;
     long long* blocksum;  // scan scratch
 };
+
+constexpr int RLAP_LIVE_DEAD = -0x40000000;
+__host__ __device__ __forceinline__ int* live_p(const SchurParams& P, size_t i) { return P.lh + 2 * i; }
+__host__ __device__ __forceinline__ int* head_p(const SchurParams& P, size_t i) { return P.lh + 2 * i + 1; }
 
 }  // namespace rlap
