@@ -229,6 +229,15 @@ def test_dirty_workspace_and_pool_retry_are_harmless(oracle_port):
                                                            pool_cap=64 if rep % 2 else 0)
                 assert np.array_equal(row.cpu().numpy(), r0) and np.array_equal(col.cpu().numpy(), c0), (o_v, full, rep)
                 assert np.array_equal(wt.cpu().numpy().view(np.uint32), w0.view(np.uint32)), (o_v, full, rep)
+    # the same through the view groups (one concurrent launch per view): every group overflows and is retried
+    for o_v in ("random", "degree", "coarsen"):
+        (row, col, wt), vp = rlap_b200.schur_views(g, 50, o_v, "asc", num_views=4, seed=7, dtype=None, pool_cap=64)
+        row, col, wt, vp = row.cpu().numpy(), col.cpu().numpy(), wt.cpu().numpy(), vp.numpy()
+        for v in range(4):
+            r0, c0, w0 = oracle_port.keyed_schur(optr, ocol, ow, 50, o_v, "asc", seed=7, view=v)
+            s, e = vp[v], vp[v + 1]
+            assert np.array_equal(row[s:e], r0) and np.array_equal(col[s:e], c0), (o_v, v)
+            assert np.array_equal(wt[s:e].view(np.uint32), w0.view(np.uint32)), (o_v, v)
 
 
 @pytest.mark.parametrize("o_v", ["degree", "coarsen"])
