@@ -28,15 +28,9 @@ __device__ __forceinline__ int graph_of(const SchurParams& P, int v) { return P.
 
 // key of the degree bucket queue (preconditioner.cc:125-246 restated): number of live
 // list entries, never below 1 once the vertex had an edge (DegreePQDec is a no-op at key 1), 0 for
-// vertices that were isolated from the start.
+// vertices that were isolated from the start; computed inline where it is needed as
+// (state == 4) ? 0 : max(live, 1).
 // state byte: 0 kept (o_v = random, not eligible), 1 pending, 2 eliminated, 4 pending and isolated from the start
-__device__ __forceinline__ int key_eff(const SchurParams& P, size_t idx, uint8_t st) {
-    if (st == 4) return 0;
-    return max(ldcg_i32(live_p(P, idx)), 1);
-}
-__device__ __forceinline__ int key_nbr(const SchurParams& P, size_t vb, int u) {  // u has an edge: deg0 > 0
-    return max(ldcg_i32(live_p(P, vb + u)), 1);
-}
 
 // ---------------------------------------------------------------------------------------------
 // star staging
