@@ -453,14 +453,26 @@ __global__ void __launch_bounds__(256) k_emit_copy(SchurParams P, int* out_row, 
     const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
     const int lane = threadIdx.x & 31;
+    // the counts and offsets of the next 32 vertices are requested before the rows of the current ones are copied
+    long long nsrc = 0, ndst = 0;
+    int nL = 0;
+    if (gw * 32 + lane < VN) {
+        nL = P.outcnt[gw * 32 + lane];
+        nsrc = P.rawoff[gw * 32 + lane];
+        ndst = P.outoff[gw * 32 + lane];
+    }
     for (long long base = gw * 32; base < VN; base += nw * 32) {
         const long long idx = base + lane;
-        long long src = 0, dst = 0;
-        int L = 0;
-        if (idx < VN) {
-            L = P.outcnt[idx];
-            src = P.rawoff[idx];
-            dst = P.outoff[idx];
+        const long long src = nsrc, dst = ndst;
+        const int L = nL;
+        {
+            const long long nidx = idx + nw * 32;
+            nL = 0; nsrc = 0; ndst = 0;
+            if (nidx < VN) {
+                nL = P.outcnt[nidx];
+                nsrc = P.rawoff[nidx];
+                ndst = P.outoff[nidx];
+            }
         }
         const long long dst0 = __shfl_sync(RLAP_FULL_MASK, dst, 0);
         // start of lane i's rows relative to the warp's output range; lanes past VN inherit the end of the range
