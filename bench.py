@@ -277,6 +277,49 @@ def run_ours(args):
         pending[slot] = pool.submit(finish, done, total, (row, col, w, g, d))
         return total
 
+    # the same with per-view column pointers instead of the col array over the link (18 instead of 26 MB per view) and
+    # col rebuilt in the pinned host buffer by host threads; pays off when several GPUs share the host's ingress
+    fill_threads = max(2, min(8, host_cores() // max(world, 1)))
+
+    def finish_colptr(done, hb, vp, total, keepalive):
+        done.synchronize()
+        del keepalive
+        ops.expand_cols(hb["colptr"], vp, out=hb["col"], threads=fill_threads)
+        return total
+
+    def step_e2e_colptr(step):
+        slot = step & 1
+        if pending[slot] is not None:
+            pending[slot].result()
+            pending[slot] = None
+        d = ei_pinned.to(dev, non_blocking=True)
+        g = ops.prepare(d, None, N_NODES)
+        (row, cp, w), vp = ops.schur_views(g, t, O_V, O_N, num_views=V, seed=1234 + step, view_base=rank * V, dtype=None,
+                                           colptr=True)
+        total = int(vp[-1])
+        hb = host_bufs[slot]
+        if "row" not in hb or hb["row"].numel() < total or "colptr" not in hb:
+            cap = int(total * 1.05)
+            hb["row"] = torch.empty(cap, dtype=torch.int32).pin_memory()
+            hb["col"] = torch.empty(cap, dtype=torch.int32).pin_memory()
+            hb["w"] = torch.empty(cap, dtype=torch.float32).pin_memory()
+            hb["colptr"] = torch.empty((V, N_NODES + 1), dtype=torch.int32).pin_memory()
+        ready = torch.cuda.Event()
+        ready.record()
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ready)
+            hb["row"][:total].copy_(row, non_blocking=True)
+            hb["w"][:total].copy_(w, non_blocking=True)
+            hb["colptr"].copy_(cp, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record()
+        d2h_bytes["n"] = total * 8 + cp.numel() * 4
+        pending[slot] = pool.submit(finish_colptr, done, hb, vp, total, (row, cp, w, g, d))
+        return total
+
+    e2e_mode = args.e2e_mode if args.e2e_mode != "auto" else ("colptr" if world >= 2 else "rows")
+    e2e_step = step_e2e_colptr if e2e_mode == "colptr" else step_e2e
+
     def drain_e2e():
         for slot in (0, 1):
             if pending[slot] is not None:
@@ -292,15 +335,15 @@ def run_ours(args):
         res = None
         for s in range(warmup):
             res = fn(s)       # same allocation pattern as the timed loop: the previous result stays alive during a step
-        if fn is step_e2e:
+        if fn is e2e_step:
             drain_e2e()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for s in range(steps):
             res = fn(warmup + s)
-        if fn is step_e2e:
-            drain_e2e()          # the last copies are part of the timed region
+        if fn is e2e_step:
+            drain_e2e()          # the last copies (and host rebuilds) are part of the timed region
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -323,7 +366,7 @@ def run_ours(args):
               "segments", torch.cuda.memory_stats().get("segment.all.allocated"), file=sys.stderr)
     n_launch = launches["n"] * args.steps // (args.steps + args.warmup)
     clocks = sampler.stop()
-    ms_e2e, total_rows = timed(step_e2e, args.steps, max(args.warmup, 1))
+    ms_e2e, total_rows = timed(e2e_step, args.steps, max(args.warmup, 1))
 
     ms_step = ms_total / args.steps
     value = world * V * args.steps / (ms_total / 1e3)
@@ -364,7 +407,13 @@ def run_ours(args):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(ei_pinned.numel() * 8),
                 "d2h_bytes_per_step": int(d2h_bytes["n"]), "ms_per_step": ms_e2e / args.steps,
-                "api": "ops.prepare + ops.schur_views from pinned host edge_index; packed rows copied back to pinned host on a copy stream, overlapping the next step (2 buffer sets)"},
+                "mode": e2e_mode,
+                "api": ("ops.prepare + ops.schur_views from pinned host edge_index; packed rows copied back to pinned host "
+                        "on a copy stream, overlapping the next step (2 buffer sets)") if e2e_mode == "rows" else
+                       ("ops.prepare + ops.schur_views(colptr=True) from pinned host edge_index; rows, weights and per-view "
+                        "column pointers copied back to pinned host on a copy stream, col rebuilt there by "
+                        f"ops.expand_cols with {fill_threads} host threads, both overlapping the next step (2 buffer sets); "
+                        "the host ends with (row, col, w) of every view")},
         "gpu_launches": int(n_launch),
         "roofline": {"bound": "hbm", "kernel": "k_eliminate", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
@@ -401,6 +450,8 @@ def main():
     ap.add_argument("--views", type=int, default=64, help="views per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-mode", default="rows", choices=["rows", "colptr", "auto"],
+                    help="what crosses the link in the e2e loop: packed rows, or rows + column pointers (col rebuilt on the host)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
