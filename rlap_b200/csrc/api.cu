@@ -480,6 +480,10 @@ int rlap_schur_eliminate(int64_t n, int64_t nnz, const int32_t* csr_ptr, const i
         for (int i = 0; i < 6; i++)
             fprintf(stderr, " %s %.0f (wait %.0f)", nm[i], hstats[ST_T_INIT + i] / 1e3, hstats[ST_W_INIT + i] / 1e3 / nwarps);
         fprintf(stderr, " | stars on the shared-memory warp path %llu\n", hstats[ST_DEFERRED]);
+        if (flags & 512)
+            fprintf(stderr, "rlap phase B, thread 0 of the slowest group (us): setup %.0f list %.0f scan %.0f flush %.0f tail %.0f barrier %.0f\n",
+                    hstats[ST_DBG] / 1e3, hstats[ST_DBG + 1] / 1e3, hstats[ST_DBG + 2] / 1e3, hstats[ST_DBG + 3] / 1e3,
+                    hstats[ST_DBG + 4] / 1e3, hstats[ST_DBG + 5] / 1e3);
     }
     {
         std::lock_guard<std::mutex> lk(g_layout_mutex);

@@ -767,6 +767,16 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
         }
         lap(slot);
     };
+    // debug (flags & 512): thread 0 of block 0 times the parts of phase B
+    unsigned long long dmark = 0;
+    auto dlap = [&](int slot) {
+        if ((P.flags & 512) && tid == 0) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (slot >= 0) P.stats[ST_DBG + slot] += now - dmark;
+            dmark = now;
+        }
+    };
     int wl_start = 0;   // first unconsumed work-list item
     int dl_start = 0;
     int rounds = 0;
@@ -1020,6 +1030,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
             // other members (and the listed vertices below the level that are not in the bucket) go to the next list.
             // Shared memory (the star buffers are idle): per-segment copies if there are few enough segments, a
             // candidate buffer per warp so that the work-list tail is bumped once per few hundred candidates.
+            dlap(-1);
             int* srem = (int*)smem;                 // remaining removals (0: the segment is done)
             int* smk = srem + SEG_SM;               // bucket key of the round (INF: nothing to do)
             int* scnt = smk + SEG_SM;               // candidates selected by this block
@@ -1122,6 +1133,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
                 }
                 wfill += __popc(cm);
             };
+            dlap(0);
             // B1: the low list (segments that do not rescan)
             for (long long i0 = tid - lane; i0 < n_in; i0 += nthr) {
                 const long long i = i0 + lane;
@@ -1147,6 +1159,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
                 select(cand, idx, seg, rm);
                 la.push(keep, idx);
             }
+            dlap(1);
             // B2: full scan of the segments that rescan; the level moves to the bucket key found
             for (long long q = tid; q < VG; q += nthr) {
                 if (ldcg_i32(mkl + q) == INF) { const int m2 = ldcg_i32(mks + q); if (m2 != INF) P.lvl[q] = m2; }
@@ -1196,8 +1209,10 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
                     }
                 }
             }
+            dlap(2);
             flush();
             la.flush();
+            dlap(3);
             if (bsm) {
                 __syncthreads();
                 for (int q = threadIdx.x; q < (int)VG; q += blockDim.x) {
@@ -1209,7 +1224,9 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
                 }
             }
             __syncthreads();   // the shared copies are star buffers again from here on
+            dlap(4);
             gsync(ST_T_B);
+            dlap(5);
             // phase C: a graph that selected more than it may still remove keeps its highest ids
             if (ldcg_i32(P.ctr + CTR_OVF0 + par)) {
                 const int gw = (int)(tid >> 5), nw = (int)(nthr >> 5), lane = threadIdx.x & 31;

@@ -48,7 +48,8 @@ struct RoundCtx {
 enum { ST_FILLS = 0, ST_POOL_MAX = 1, ST_MAXSTAR = 2, ST_DEFERRED = 3, ST_RAW = 4,
        ST_T_INIT = 8, ST_T_A = 9, ST_T_B = 10, ST_T_C = 11, ST_T_D1 = 12, ST_T_D2 = 13,
        ST_W_INIT = 16 /* .. 21: warp-nanoseconds spent waiting at the grid barrier that ends each phase (flags & 128) */,
-       ST_COUNT = 24 };
+       ST_DBG = 24 /* .. 29: debug (flags & 512): thread 0's time in the parts of phase B (setup, list, scan, flush), ns */,
+       ST_COUNT = 32 };
 
 struct SchurParams {
     // coalesced graph (shared by all views, immutable)
