@@ -862,7 +862,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
         // (bucket members that were blocked, listed vertices that were not in the bucket, and every vertex whose
         // live counter was seen crossing from above lvl to lvl or below by the elimination phase). While the low
         // list of a segment has an entry in play the bucket is taken from the list alone.
-        constexpr int SEG_SM = 1024, WBUF = 320;
+        constexpr int SEG_SM = 1024, WBUF = 224, MBUF = 160;
         const int INF = 0x7fffffff;
         // (round, key) snapshots written by phase A, read by the bucket test of phase B; the emission's row offsets
         // are not needed before the elimination is over
@@ -1133,6 +1133,26 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
                 }
                 wfill += __popc(cm);
             };
+            // member buffer of the scan part: up to 32 left over + 128 new per iteration
+            unsigned int* mbuf = (unsigned int*)((int*)smem + 6 * SEG_SM + WARPS_PER_BLOCK * WBUF) + (size_t)(threadIdx.x >> 5) * MBUF;
+            int mfill = 0;
+            auto test_members = [&](int first, int count) {      // warp-collective: lane i tests member first + i
+                bool cand = false, keep = false;
+                unsigned idx = 0;
+                int seg = 0, rm = 0;
+                if (lane < count) {
+                    idx = mbuf[first + lane];
+                    const int view = (int)(idx / un), v = (int)(idx % un);
+                    seg = view * P.G + graph_of(P, v);
+                    int m, lvq;
+                    bool scan;
+                    seg_round(seg, rm, m, scan, lvq);
+                    if (member_free(idx, view, v, m)) cand = true; else keep = true;
+                }
+                __syncwarp();
+                select(cand, idx, seg, rm);
+                la.push(keep, idx);
+            };
             dlap(0);
             // B1: the low list (segments that do not rescan)
             for (long long i0 = tid - lane; i0 < n_in; i0 += nthr) {
@@ -1196,18 +1216,22 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
                             }
                         }
                     }
+                    // the bucket members among these 128 vertices go to the warp's member buffer; the tests run on full
+                    // batches of 32 members, one per lane (testing in place left three quarters of the lanes idle while
+                    // the warp waited for the longest list of each of the four passes)
 #pragma unroll
                     for (int q4 = 0; q4 < 4; q4++) {
                         const unsigned idx = (unsigned)vw4[q4] * un + (unsigned)vx4[q4];
                         const int m = mk4[q4];
-                        bool cand = false, keep = false;
-                        if (m >= 0 && st4[q4] != 2 && ((st4[q4] == 4) ? 0 : max(lv4[q4], 1)) == m) {
-                            if (member_free(idx, vw4[q4], vx4[q4], m)) cand = true; else keep = true;
-                        }
-                        select(cand, idx, sg4[q4], rm4[q4]);
-                        la.push(keep, idx);
+                        const bool member = m >= 0 && st4[q4] != 2 && ((st4[q4] == 4) ? 0 : max(lv4[q4], 1)) == m;
+                        const unsigned mm = __ballot_sync(RLAP_FULL_MASK, member);
+                        if (member) mbuf[mfill + __popc(mm & lt)] = idx;
+                        mfill += __popc(mm);
                     }
+                    __syncwarp();
+                    while (mfill >= 32) { mfill -= 32; test_members(mfill, 32); }
                 }
+                if (mfill > 0) { test_members(0, mfill); mfill = 0; }
             }
             dlap(2);
             flush();
