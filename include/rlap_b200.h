@@ -53,7 +53,9 @@ enum { RLAP_ON_ASC = 0, RLAP_ON_DESC = 1, RLAP_ON_RANDOM = 2 };
 enum {
     RLAP_FLAG_FULL_CLIQUE = 1,   /* replace sampling by full clique elimination: exact Schur complement */
     RLAP_FLAG_SHARED_ORDER = 2,  /* o_v=random: all views share view 0's vertex permutation              */
-    RLAP_FLAG_NO_VALIDATE = 4    /* rlap_ingest: skip the symmetry check                                 */
+    RLAP_FLAG_NO_VALIDATE = 4,   /* rlap_ingest: skip the symmetry check                                 */
+    RLAP_FLAG_CHECK_LIVE = 8     /* self-check: count the surviving vertices whose emitted entry count differs
+                                    from the live counter the elimination maintained (stats[15], must be 0)  */
 };
 
 const char* rlap_status_string(int status);
@@ -79,7 +81,8 @@ int rlap_ingest(const int64_t* src, const int64_t* dst, const float* w, int64_t 
  * pure function of (seed, view id, vertex, neighbour), so results do not depend on how views are
  * sharded over GPUs). graph_ptr: HOST int64[n_graphs+1]; num_remove: HOST int64[n_graphs].
  * pool_cap: fill-edge pool entries per view (0 = default 2*nnz + 4096). scratch_cap: largest star
- * (raw live entries) the global scratch path accepts (0 = default min(n, 1<<20)).
+ * (raw live entries) the global scratch path accepts (0 = default min(n, 65536); a larger star returns
+ * RLAP_ERR_STAR_TOO_LARGE and the caller retries with scratch_cap = nnz + 1, as rlap_approximate_cholesky_host does).
  * After rlap_schur_eliminate returns, view_rows (HOST int64[n_views]) holds the number of output
  * rows of every view. Synchronises `stream` once. */
 int rlap_schur_workspace_bytes(int64_t n, int64_t nnz, int64_t n_graphs, int64_t n_views, int64_t pool_cap,
@@ -93,7 +96,7 @@ int rlap_schur_eliminate(int64_t n, int64_t nnz, const int32_t* csr_ptr, const i
  * [4] raw adjacency entries read at elimination, [5] output rows, [6] pool_cap used,
  * [7] elimination kernel time (us, CUDA events), [8] emission count pass time (us),
  * [9..14] time inside the elimination kernel (us): init, min-key scan, candidate selection, truncation,
- * warp-level elimination, block-level elimination; [15] (only with RLAP_DEBUG_CHECK=1 in the environment) number of
+ * warp-level elimination, block-level elimination; [15] (only with RLAP_FLAG_CHECK_LIVE) number of
  * surviving vertices whose scattered entry count differs from their live counter: must be 0. */
 
 /* ---- emission (replaces the output assembly, preconditioner.cc:435-457 / 789-810 / 916-934) ------
@@ -118,6 +121,11 @@ int rlap_schur_emit(int64_t n, int64_t nnz, const int32_t* csr_ptr, const int32_
  * leaves the host (py_api_binder.cc:54-69). */
 int rlap_schur_colptr(int64_t n, int64_t nnz, int64_t n_views, void* workspace, size_t workspace_bytes,
                       int32_t* colptr, void* stream);
+
+/* Forget the results rlap_schur_eliminate left in `workspace`. Call it before the workspace memory is freed or
+ * reused: rlap_schur_emit / rlap_schur_colptr refuse a workspace that was released (the library keeps no
+ * reference to caller memory afterwards). No reference counterpart (the reference returns one heap matrix). */
+int rlap_schur_release(void* workspace);
 int rlap_expand_cols_host(const int32_t* colptr, int64_t n_views, int64_t n, const int64_t* view_ptr, int32_t* out_col,
                           int n_threads);
 

@@ -577,6 +577,10 @@ static void order_star(Star& s, int o_n) {
 }
 
 struct Stats { int64_t D = 0, F = 0, maxlen = 0, rounds = 0, Draw = 0; };
+// optional histograms of the raw / merged star sizes (oracle_set_hist): [0..63] exact, [64] = 64 and above
+static int64_t* g_hist_raw = nullptr;
+static int64_t* g_hist_len = nullptr;
+static int64_t* g_emit_counts = nullptr;   // optional [4]: survivors with entries, with a multi-edge, raw entries, merged rows
 
 static void add_edge(Graph& g, int32_t a, int32_t b, float w) {
     g.adj[(size_t)a].push_back(Entry{b, w});
@@ -592,6 +596,8 @@ static void eliminate(Graph& g, int32_t i, int o_v, int o_n, int flags, const Ph
     st.D += s.lraw;
     int64_t L = (int64_t)s.m.size();
     st.maxlen = std::max(st.maxlen, L);
+    if (g_hist_raw) g_hist_raw[std::min<int64_t>(s.lraw, 64)]++;
+    if (g_hist_len) g_hist_len[std::min<int64_t>(L, 64)]++;
     for (Merged& mm : s.m) {
         uint32_t o[4];
         ph((uint32_t)i, (uint32_t)mm.nbr, view, TAG_STAR, o);
@@ -788,6 +794,12 @@ int64_t oracle_keyed_schur(int64_t n, const int64_t* ptr, const int32_t* col, co
     for (int64_t v = 0; v < n; v++) {
         if (g.elim[(size_t)v]) continue;
         gather_star(g, (int32_t)v, s);
+        if (keyed::g_emit_counts && s.lraw > 0) {
+            keyed::g_emit_counts[0]++;
+            if ((int64_t)s.m.size() != s.lraw) keyed::g_emit_counts[1]++;
+            keyed::g_emit_counts[2] += s.lraw;
+            keyed::g_emit_counts[3] += (int64_t)s.m.size();
+        }
         for (const Merged& mm : s.m) {
             if (rows < out_cap) { out_row[rows] = mm.nbr; out_col[rows] = (int32_t)v; out_w[rows] = mm.wf; }
             rows++;
@@ -798,6 +810,10 @@ int64_t oracle_keyed_schur(int64_t n, const int64_t* ptr, const int32_t* col, co
 }
 
 }  // extern "C"
+
+// histograms of the star sizes seen by the keyed eliminations that follow (65 bins each; nullptr switches them off)
+extern "C" void oracle_set_hist(int64_t* raw, int64_t* len) { keyed::g_hist_raw = raw; keyed::g_hist_len = len; }
+extern "C" void oracle_set_emit_counts(int64_t* c) { keyed::g_emit_counts = c; }
 
 extern "C" void oracle_rank_perm(uint64_t seed, uint32_t graph, uint32_t view, uint32_t n_g, uint32_t* out) {
     keyed::Philox ph{(uint32_t)seed, (uint32_t)(seed >> 32)};

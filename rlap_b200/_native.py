@@ -14,11 +14,13 @@ ON = {"asc": 0, "desc": 1, "random": 2}
 FLAG_FULL_CLIQUE = 1
 FLAG_SHARED_ORDER = 2
 FLAG_NO_VALIDATE = 4
+FLAG_CHECK_LIVE = 8
+RLAP_ERR_STAR_TOO_LARGE = 6
 
 EXPORTS = [
     "rlap_status_string", "rlap_last_cuda_error", "rlap_version", "rlap_ingest_workspace_bytes", "rlap_ingest",
     "rlap_schur_workspace_bytes", "rlap_schur_eliminate", "rlap_schur_emit", "rlap_approximate_cholesky_host",
-    "rlap_free_host", "rlap_schur_colptr", "rlap_expand_cols_host",
+    "rlap_free_host", "rlap_schur_colptr", "rlap_expand_cols_host", "rlap_schur_release",
 ]
 
 
@@ -57,6 +59,7 @@ def lib():
                                                  ctypes.POINTER(i64)]
     L.rlap_schur_colptr.argtypes = [i64, i64, i64, P, sz, P, P]
     L.rlap_expand_cols_host.argtypes = [P, i64, i64, P, P, ctypes.c_int]
+    L.rlap_schur_release.argtypes = [P]
     L.rlap_free_host.argtypes = [P]
     L.rlap_free_host.restype = None
     for name in EXPORTS:

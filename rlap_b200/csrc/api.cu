@@ -63,7 +63,27 @@ struct Mailbox {
         return 0;
     }
 };
-static thread_local Mailbox g_mail;
+
+// Streams, events and the mailbox belong to the device that was current when they were created: one set per
+// (host thread, device), created on first use on that device.
+constexpr int MAX_GROUPS = 64;
+struct ThreadDevice {
+    Mailbox mail;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    cudaStream_t gs[MAX_GROUPS] = {nullptr};
+    cudaEvent_t gev[MAX_GROUPS + 1] = {nullptr};
+    std::vector<int> gp;
+};
+static ThreadDevice* thread_device() {
+    static thread_local std::unordered_map<int, ThreadDevice*> per_dev;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    auto it = per_dev.find(dev);
+    if (it != per_dev.end()) return it->second;
+    ThreadDevice* td = new ThreadDevice();   // lives as long as the thread's CUDA context use: never freed
+    per_dev[dev] = td;
+    return td;
+}
 
 __global__ void k_export_ingest(const int* status, const long long* total, const double* acc, long long* out) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
@@ -122,9 +142,11 @@ const char* rlap_last_cuda_error(void) { return g_last_cuda_error.c_str(); }
 int rlap_version(void) { return 1; }
 
 // ------------------------------------------------------------------------------------------ ingest
+// largest raw row the global-scratch path of the ingest accepts: a row can hold every input entry (duplicates
+// included), so the bound is e, not n
 static long long ingest_scratch_cap(long long n, long long e) {
-    long long c = n > 4096 ? n : 4096;
-    if (c > e) c = e;
+    (void)n;
+    long long c = e;
     if (c < CAP_CTA + 1) c = CAP_CTA + 1;
     return c;
 }
@@ -193,6 +215,9 @@ int rlap_ingest(const int64_t* src, const int64_t* dst, const float* w, int64_t 
     CK(cudaMemsetAsync(L.zero_begin, 0, L.zero_bytes, stream));
     CK(launch_ingest_stage1(P, stream));
     struct { int status; long long total; double acc[2]; } h;
+    ThreadDevice* td = thread_device();
+    if (!td) return cuda_fail(cudaErrorInvalidDevice, "cudaGetDevice");
+    Mailbox& g_mail = td->mail;
     if (g_mail.ensure(8)) return cuda_fail(cudaErrorMemoryAllocation, "cudaHostAlloc(mailbox)");
     k_export_ingest<<<1, 32, 0, stream>>>(P.status, P.total_dev, P.sym_acc, g_mail.host);
     CK(cudaGetLastError());
@@ -228,8 +253,6 @@ struct SchurLayout {
 // own share of the SMs and with its own grid barrier: views are independent, and a barrier over all of them makes
 // every phase of every view wait for the slowest chain of any view (45 % of the warp time in the single-launch
 // profile, profiles/README.md).
-constexpr int MAX_GROUPS = 64;
-
 static long long default_pool_cap(long long nnz) { return 2 * nnz + 4096; }
 static long long default_scratch_cap(long long n) {
     long long c = n < 65536 ? n : 65536;
@@ -355,10 +378,13 @@ int rlap_schur_eliminate(int64_t n, int64_t nnz, const int32_t* csr_ptr, const i
     P.k0 = (uint32_t)seed;
     P.k1 = (uint32_t)(seed >> 32);
     P.view_base = (uint32_t)view_base;
+    ThreadDevice* td = thread_device();
+    if (!td) return cuda_fail(cudaErrorInvalidDevice, "cudaGetDevice");
+    Mailbox& g_mail = td->mail;
     {
         // the converted graph pointers live until the next call of this thread; this call synchronises the stream
         // before it returns, so no extra synchronisation (which would drain the caller's queued work) is needed here
-        static thread_local std::vector<int> gp;
+        std::vector<int>& gp = td->gp;
         gp.resize((size_t)n_graphs + 1);
         for (int64_t g = 0; g <= n_graphs; g++) gp[(size_t)g] = (int)graph_ptr[g];
         CK(cudaMemcpyAsync(L.gptr_dev, gp.data(), sizeof(int) * gp.size(), cudaMemcpyHostToDevice, stream));
@@ -369,16 +395,17 @@ int rlap_schur_eliminate(int64_t n, int64_t nnz, const int32_t* csr_ptr, const i
     CK(launch_setup_graphs((int)n, (int)n_graphs, L.gptr_dev, L.nrem_dev, n_graphs > 1 ? L.gid_dev : nullptr, L.teff_dev,
                            stream));
     // device-side timing of the two phases (read back with the counts; no extra synchronisation)
-    static thread_local cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t* ev = td->ev;
     if (!ev[0]) for (int i = 0; i < 3; i++) CK(cudaEventCreate(&ev[i]));
     CK(cudaEventRecord(ev[0], stream));
     {
         // view groups: K concurrent cooperative launches, each on blocks / K blocks
         int blocks = 0;
         CK(eliminate_grid(&blocks));
-        long long K = 1;
-        if (const char* env = getenv("RLAP_GROUPS")) K = atoll(env);
-        else K = n_views / ((n_views + 31) / 32);        // at most 32 groups (about 9 blocks each), equal shares of views
+        long long K = n_views / ((n_views + 31) / 32);   // at most 32 groups (about 9 blocks each), equal shares of views
+#ifdef RLAP_DEBUG
+        if (const char* env = getenv("RLAP_GROUPS")) { K = atoll(env); }
+#endif
         if (K > n_views) K = n_views;
         if (K > MAX_GROUPS) K = MAX_GROUPS;
         if (K > blocks / 2) K = blocks / 2;
@@ -386,8 +413,8 @@ int rlap_schur_eliminate(int64_t n, int64_t nnz, const int32_t* csr_ptr, const i
         if (K == 1) {
             CK(launch_eliminate(P, stream, 0));
         } else {
-            static thread_local cudaStream_t gs[MAX_GROUPS] = {nullptr};
-            static thread_local cudaEvent_t gev[MAX_GROUPS + 1] = {nullptr};
+            cudaStream_t* gs = td->gs;
+            cudaEvent_t* gev = td->gev;
             for (long long g = 0; g < K; g++) {
                 if (!gs[g]) CK(cudaStreamCreateWithFlags(&gs[g], cudaStreamNonBlocking));
                 if (!gev[g]) CK(cudaEventCreateWithFlags(&gev[g], cudaEventDisableTiming));
@@ -426,10 +453,12 @@ int rlap_schur_eliminate(int64_t n, int64_t nnz, const int32_t* csr_ptr, const i
             CK(launch_combine_groups((int)K, L.gctr, L.gstats, P.ctr, P.stats, stream));
         }
     }
+#ifdef RLAP_DEBUG
     if (getenv("RLAP_DEBUG_SYNC")) {
         cudaError_t de = cudaStreamSynchronize(stream);
         if (de != cudaSuccess) return cuda_fail(de, "k_eliminate (debug sync)");
     }
+#endif
     CK(cudaEventRecord(ev[1], stream));
     CK(launch_emit_count(P, L.total_dev, stream));
     CK(cudaEventRecord(ev[2], stream));
@@ -468,9 +497,9 @@ int rlap_schur_eliminate(int64_t n, int64_t nnz, const int32_t* csr_ptr, const i
         stats[7] = (int64_t)(ms_elim * 1000.0f);   // k_eliminate, microseconds
         stats[8] = (int64_t)(ms_count * 1000.0f);  // emission count pass + scan, microseconds
         for (int i = 0; i < 6; i++) stats[9 + i] = (int64_t)(hstats[ST_T_INIT + i] / 1000);  // phase times, us
-        stats[15] = (int64_t)hstats[7];  // debug check: vertices whose scattered count != live counter
-        if (hstats[7]) fprintf(stderr, "rlap debug: %llu live/scatter mismatches, last idx %llu scattered %llu live %llu\n", hstats[7], hstats[6] >> 32, (hstats[6] >> 16) & 0xffff, hstats[6] & 0xffff);
+        stats[15] = (int64_t)hstats[7];  // RLAP_FLAG_CHECK_LIVE: vertices whose scattered count != live counter
     }
+#ifdef RLAP_DEBUG
     if ((flags & 128) && getenv("RLAP_DEBUG_TIMERS")) {   // mean barrier wait per warp and phase, microseconds
         int blocks = 0;
         eliminate_grid(&blocks);
@@ -485,9 +514,12 @@ int rlap_schur_eliminate(int64_t n, int64_t nnz, const int32_t* csr_ptr, const i
                     hstats[ST_DBG] / 1e3, hstats[ST_DBG + 1] / 1e3, hstats[ST_DBG + 2] / 1e3, hstats[ST_DBG + 3] / 1e3,
                     hstats[ST_DBG + 4] / 1e3, hstats[ST_DBG + 5] / 1e3);
     }
+#endif
     {
+        // the layout is what rlap_schur_emit / rlap_schur_colptr need to find the results in the workspace; a failed
+        // run leaves nothing to emit
         std::lock_guard<std::mutex> lk(g_layout_mutex);
-        g_layouts[workspace] = L;
+        if (hctr[CTR_STATUS] != 0) g_layouts.erase(workspace); else g_layouts[workspace] = L;
     }
     if (hctr[CTR_STATUS] != 0) return hctr[CTR_STATUS];
     return RLAP_OK;
@@ -509,6 +541,12 @@ int rlap_schur_emit(int64_t n, int64_t nnz, const int32_t* csr_ptr, const int32_
     if ((out_row || out_col || out_w) && !(out_row && out_w)) return RLAP_ERR_INVALID_ARG;   // out_col alone may be NULL
     if (!out_row && !out_f64) return RLAP_ERR_INVALID_ARG;
     CK(launch_emit_write(L.P, out_row, out_col, out_w, out_f64, stream));
+    return RLAP_OK;
+}
+
+int rlap_schur_release(void* workspace) {
+    std::lock_guard<std::mutex> lk(g_layout_mutex);
+    g_layouts.erase(workspace);
     return RLAP_OK;
 }
 
@@ -591,16 +629,19 @@ int rlap_approximate_cholesky_host(const double* edge_info, int64_t e, int64_t n
     int ov = !strcmp(o_v, "random") ? 0 : !strcmp(o_v, "degree") ? 1 : !strcmp(o_v, "coarsen") ? 2 : -1;
     int on = !strcmp(o_n, "asc") ? 0 : !strcmp(o_n, "desc") ? 1 : !strcmp(o_n, "random") ? 2 : -1;
     if (ov < 0 || on < 0) return RLAP_ERR_INVALID_ARG;
-    static bool pool_set = false;
-    if (!pool_set) {  // keep freed blocks cached in the default pool: repeated calls do not hit cudaMalloc
+    {   // keep freed blocks cached in the device's default pool: repeated calls do not hit cudaMalloc
+        static std::mutex mu;
+        static PerDeviceOnce once;
         int dev = 0;
         cudaGetDevice(&dev);
-        cudaMemPool_t mp;
-        if (cudaDeviceGetDefaultMemPool(&mp, dev) == cudaSuccess) {
-            uint64_t thr = UINT64_MAX;
-            cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &thr);
+        std::lock_guard<std::mutex> lk(mu);
+        if (once.first(dev)) {
+            cudaMemPool_t mp;
+            if (cudaDeviceGetDefaultMemPool(&mp, dev) == cudaSuccess) {
+                uint64_t thr = UINT64_MAX;
+                cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &thr);
+            }
         }
-        pool_set = true;
     }
     cudaStream_t s = 0;
     *out = nullptr;
@@ -631,17 +672,26 @@ int rlap_approximate_cholesky_host(const double* edge_info, int64_t e, int64_t n
     int64_t gp[2] = {0, n};
     int64_t nr[1] = {num_remove};
     int64_t vrows = 0;
-    int64_t pool_cap = 0;
+    int64_t pool_cap = 0, scratch_cap = 0;
     size_t wsb2 = 0;
+    struct Release {   // the registered layout must not outlive the workspace, whatever the exit path
+        void* ws;
+        ~Release() { rlap_schur_release(ws); }
+    };
     for (int attempt = 0;; attempt++) {
-        st = rlap_schur_workspace_bytes(n, nnz, 1, 1, pool_cap, 0, 0, &wsb2);
+        st = rlap_schur_workspace_bytes(n, nnz, 1, 1, pool_cap, scratch_cap, 0, &wsb2);
         if (st) return st;
         DevBuf ws2(s);
         CK(ws2.alloc(wsb2));
+        Release rel{ws2.p};
         st = rlap_schur_eliminate(n, nnz, (int32_t*)d_ptr.p, (int32_t*)d_col.p, (float*)d_cw.p, 1, gp, nr, ov, on, seed,
-                                  0, 1, 0, pool_cap, 0, ws2.p, wsb2, &vrows, nullptr, s);
+                                  0, 1, 0, pool_cap, scratch_cap, ws2.p, wsb2, &vrows, nullptr, s);
         if (st == RLAP_ERR_POOL_OVERFLOW && attempt < 6) {
             pool_cap = (pool_cap ? pool_cap : 2 * nnz + 4096) * 2;
+            continue;
+        }
+        if (st == RLAP_ERR_STAR_TOO_LARGE && scratch_cap == 0) {   // a star beyond the default scratch: a star never exceeds nnz entries
+            scratch_cap = nnz + 1;
             continue;
         }
         if (st) return st;
@@ -651,12 +701,9 @@ int rlap_approximate_cholesky_host(const double* edge_info, int64_t e, int64_t n
         if (st) return st;
         double* h = (double*)malloc(sizeof(double) * 3 * (size_t)(vrows > 0 ? vrows : 1));
         if (!h) return RLAP_ERR_INVALID_ARG;
-        CK(cudaMemcpyAsync(h, d_out.p, sizeof(double) * 3 * (size_t)vrows, cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
-        {
-            std::lock_guard<std::mutex> lk(g_layout_mutex);
-            g_layouts.erase(ws2.p);
-        }
+        cudaError_t ce = cudaMemcpyAsync(h, d_out.p, sizeof(double) * 3 * (size_t)vrows, cudaMemcpyDeviceToHost, s);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+        if (ce != cudaSuccess) { free(h); return cuda_fail(ce, "copy of the result to the host"); }
         *out = h;
         *rows = vrows;
         return RLAP_OK;

@@ -12,6 +12,7 @@
 //                                                       -> scan -> outoff
 //   k_emit_copy     compact copy into the caller's buffers (packed and/or [E',3] float64)
 #include <stdlib.h>
+#include <mutex>
 #include "rlap_device.cuh"
 #include "schur.cuh"
 #include "scan.cuh"
@@ -125,7 +126,7 @@ __global__ void __launch_bounds__(256) k_emit_scatter(SchurParams P) {
     }
 }
 
-// debug (RLAP_DEBUG_CHECK=1): every survivor's scattered entry count must equal its live counter
+// RLAP_FLAG_CHECK_LIVE: every survivor's scattered entry count must equal its live counter (self-check, stats[15])
 __global__ void k_emit_check(SchurParams P) {
     const long long VN = (long long)P.V * P.n;
     long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -527,13 +528,18 @@ __global__ void k_emit_colptr(SchurParams P, int* colptr) {
 cudaError_t eliminate_grid(int* blocks_out);
 
 cudaError_t launch_emit_count(const SchurParams& P, long long* total_dev, cudaStream_t stream) {
-    static bool attr_done = false;
     const size_t smem = (size_t)3 * CAP_CTA * sizeof(uint64_t);
     const size_t smem_big = (size_t)2 * CAP_BIG * sizeof(uint64_t);
-    if (!attr_done) {
-        cudaFuncSetAttribute(k_emit_sort_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(k_emit_sort_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big);
-        attr_done = true;
+    {
+        static std::mutex mu;
+        static PerDeviceOnce once;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        std::lock_guard<std::mutex> lk(mu);
+        if (once.first(dev)) {
+            cudaFuncSetAttribute(k_emit_sort_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(k_emit_sort_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big);
+        }
     }
     const long long VN = (long long)P.V * P.n;
     cudaError_t e = cudaMemsetAsync(P.ctr + CTR_EMIT_C0, 0, N_CLASS * sizeof(int), stream);
@@ -552,7 +558,7 @@ cudaError_t launch_emit_count(const SchurParams& P, long long* total_dev, cudaSt
         if (bx > 148 * 8) bx = 148 * 8;
         k_emit_scatter<<<dim3((unsigned)bx, (unsigned)P.V), 256, 0, stream>>>(P);
     }
-    if (getenv("RLAP_DEBUG_CHECK")) k_emit_check<<<(unsigned)((VN + 255) / 256), 256, 0, stream>>>(P);
+    if (P.flags & 8) k_emit_check<<<(unsigned)((VN + 255) / 256), 256, 0, stream>>>(P);   // RLAP_FLAG_CHECK_LIVE
     int blocks = 0;
     e = eliminate_grid(&blocks);
     if (e != cudaSuccess) return e;

@@ -9,6 +9,7 @@
 #include "rlap_device.cuh"
 #include "schur.cuh"
 #include "scan.cuh"
+#include <mutex>
 #include "ingest.cuh"
 
 namespace rlap {
@@ -202,12 +203,17 @@ cudaError_t launch_ingest_stage1(const IngestParams& P, cudaStream_t stream) {
     cudaError_t e = launch_exclusive_scan<int>(P.cnt, P.n, P.rawptr, P.blocksum, nullptr, stream);
     if (e != cudaSuccess) return e;
     k_ingest_scatter<<<grid_for(P.e, 256, 148 * 16), 256, 0, stream>>>(P);
-    static bool attr = false;
     const size_t smem = (size_t)3 * CAP_CTA * sizeof(uint64_t);
-    if (!attr) {
-        cudaFuncSetAttribute(k_ingest_rows_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(k_ingest_rows_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr = true;
+    {
+        static std::mutex mu;
+        static PerDeviceOnce once;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        std::lock_guard<std::mutex> lk(mu);
+        if (once.first(dev)) {
+            cudaFuncSetAttribute(k_ingest_rows_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(k_ingest_rows_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        }
     }
     int blocks = grid_for((P.n + 31) / 32 * 32, BLOCK_THREADS / 32 * 32, 148 * 2);
     k_ingest_rows_warp<<<blocks, BLOCK_THREADS, smem, stream>>>(P);

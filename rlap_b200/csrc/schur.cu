@@ -15,6 +15,7 @@
 // and DESIGN.md §3.
 #include <cooperative_groups.h>
 #include <stdio.h>
+#include <mutex>
 #include "rlap_device.cuh"
 #include "schur.cuh"
 #include "scan.cuh"
@@ -25,6 +26,17 @@ namespace cg = cooperative_groups;
 namespace rlap {
 
 __device__ __forceinline__ int graph_of(const SchurParams& P, int v) { return P.gid ? __ldg(P.gid + v) : 0; }
+
+// The kernel is compiled once per (vertex order, neighbour order, full-clique) combination: the members below hide
+// the run-time fields of the same name, so every `P.o_v == 0` in the device code is decided at compile time and an
+// instantiation carries only its own branch of the star arithmetic (half the register spills of the generic kernel,
+// ptxas -v). Same layout as SchurParams: the host passes a plain SchurParams.
+template <int OV, int ON, bool FULL>
+struct ModeParams : SchurParams {
+    static constexpr int o_v = OV;
+    static constexpr int o_n = ON;
+    static constexpr bool full = FULL;
+};
 
 // key of the degree bucket queue (preconditioner.cc:125-246 restated): number of live
 // list entries, never below 1 once the vertex had an edge (DegreePQDec is a no-op at key 1), 0 for
@@ -38,8 +50,8 @@ __device__ __forceinline__ int graph_of(const SchurParams& P, int v) { return P.
 
 // Gather the raw live entries of v into sb.A (unordered). Returns their count (group uniform);
 // *wmaxb receives the bit pattern of the largest weight. Entries beyond sb.cap are counted, not stored.
-template <bool CTA>
-__device__ int star_gather(const SchurParams& P, int view, int v, StarBuf sb, CtaScratch* cs, uint32_t* wmaxb_out) {
+template <bool CTA, class PT>
+__device__ int star_gather(const PT& P, int view, int v, StarBuf sb, CtaScratch* cs, uint32_t* wmaxb_out) {
     const size_t vb = (size_t)view * (size_t)P.n;
     const uint8_t* st = P.state + vb;
     const int4* pool = P.pool + (size_t)view * (size_t)P.pool_cap;
@@ -124,31 +136,39 @@ __device__ int star_gather(const SchurParams& P, int view, int v, StarBuf sb, Ct
 constexpr int LOWBUF = 64;
 struct LowAppender {
     unsigned int* buf = nullptr;   // [LOWBUF] shared memory, one per warp
-    unsigned int* dst = nullptr;   // nullptr: disabled (o_v = random)
-    long long cap = 0;
-    int* tail = nullptr;
-    int* ovf = nullptr;
+    const SchurParams* P = nullptr;
+    int par = -1;                  // parity of the list being written (-1: disabled, o_v = random)
     int fill = 0;
+    __device__ __forceinline__ unsigned int* dst() const { return P->low + (size_t)par * (size_t)P->low_cap; }
+    __device__ __forceinline__ int* tail() const { return P->ctr + CTR_LOW0 + par; }
+    __device__ __forceinline__ int* ovf() const { return P->ctr + CTR_LOWOVF0 + par; }
     __device__ __forceinline__ void flush() {
         if (fill == 0) return;
         const int lane = threadIdx.x & 31;
         int pos0 = 0;
-        if (lane == 0) pos0 = atomicAdd(tail, fill);
+        if (lane == 0) pos0 = atomicAdd(tail(), fill);
         pos0 = __shfl_sync(RLAP_FULL_MASK, pos0, 0);
         __syncwarp();
+        unsigned int* d = dst();
         for (int i = lane; i < fill; i += 32) {
-            if ((long long)pos0 + i < cap) dst[pos0 + i] = buf[i]; else *ovf = 1;
+            if ((long long)pos0 + i < P->low_cap) d[pos0 + i] = buf[i]; else *ovf() = 1;
         }
         __syncwarp();
         fill = 0;
     }
     __device__ __forceinline__ void push(bool pred, unsigned int val) {
-        if (dst == nullptr) return;
+        if (par < 0) return;
         const unsigned m = __ballot_sync(RLAP_FULL_MASK, pred);
         if (m == 0) return;
         if (fill + 32 > LOWBUF) flush();
         if (pred) buf[fill + __popc(m & ((1u << (threadIdx.x & 31)) - 1u))] = val;
         fill += __popc(m);
+    }
+    // one entry from one lane, outside any warp-collective pattern (rare paths)
+    __device__ __forceinline__ void push_single(unsigned int val) const {
+        if (par < 0) return;
+        const int pos = atomicAdd(tail(), 1);
+        if ((long long)pos < P->low_cap) dst()[pos] = val; else *ovf() = 1;
     }
 };
 
@@ -172,8 +192,8 @@ struct PendingPush {
 // fill edge (j,k,w): append to both endpoints; o_v = random also records the new dependency.
 // LIVE: bump the live counters of both endpoints here (the register tiles apply net deltas instead).
 // Returns false for an underflowed fill (weight 0: not created).
-template <bool LIVE>
-__device__ __forceinline__ bool push_fill(const SchurParams& P, size_t vb, int4* pool, int j, int k, float w,
+template <bool LIVE, class PT>
+__device__ __forceinline__ bool push_fill(const PT& P, size_t vb, int4* pool, int j, int k, float w,
                                           long long slot, PendingPush* pend = nullptr) {
     if (!(w > 0.f)) {  // underflowed fill: leave two tombstones so that the pool can be read linearly
         pool[slot] = make_int4(-1, 0, -1, -1);
@@ -204,11 +224,12 @@ __device__ __forceinline__ bool push_fill(const SchurParams& P, size_t vb, int4*
 }
 
 // Eliminate vertex v of `view` (A.2 clique sampling / A.4 coarsening / full clique), DESIGN.md §3.3.
-struct LocalStats { unsigned long long fills = 0, raw = 0; int maxstar = 0; unsigned nsm = 0; };
+// one record per warp in shared memory, updated by one lane at a time (kept out of the registers of the persistent kernel)
+struct LocalStats { unsigned long long fills, raw; int maxstar; unsigned nsm; };
 
-template <bool CTA>
-__device__ void eliminate_star(const SchurParams& P, const RoundCtx& rc, int view, int v, StarBuf sb, CtaScratch* cs,
-                               LocalStats& ls, LowAppender& la) {
+template <bool CTA, class PT>
+__device__ void eliminate_star(const PT& P, const RoundCtx& rc, int view, int v, StarBuf sb, CtaScratch* cs,
+                               LocalStats* ls, LowAppender& la) {
     const size_t vb = (size_t)view * (size_t)P.n;
     const int gs = g_size<CTA>(), r = g_rank<CTA>();
     const uint32_t view_id = P.view_base + (uint32_t)view;
@@ -225,7 +246,7 @@ __device__ void eliminate_star(const SchurParams& P, const RoundCtx& rc, int vie
     if (lraw > 0) {
         const int shift = star_shift(__uint_as_float(wmaxb), lraw);
         L = star_sort_merge<CTA>(sb, lraw, shift, cs, &P2);
-        const bool full = (P.flags & 1) != 0;
+        const bool full = P.full;
         const bool coarsen = (P.o_v == 2) && !full;
         const int on = coarsen ? 2 : P.o_n;
         if (!full && (on == 2 || L > 16)) {   // shuffle key; for asc / desc the tie-break of stars with > 16 neighbours
@@ -334,9 +355,9 @@ __device__ void eliminate_star(const SchurParams& P, const RoundCtx& rc, int vie
             la.push(cross, (unsigned int)(vb + (size_t)u));
         }
         if (r == 0) {
-            ls.fills += (unsigned long long)(ovf ? 0 : nf);
-            ls.maxstar = max(ls.maxstar, L);
-            ls.raw += (unsigned long long)lraw;
+            ls->fills += (unsigned long long)(ovf ? 0 : nf);
+            ls->maxstar = max(ls->maxstar, L);
+            ls->raw += (unsigned long long)lraw;
         }
     }
     if (r == 0) { P.state[vb + v] = 2; *live_p(P, vb + v) = RLAP_LIVE_DEAD; }
@@ -349,10 +370,10 @@ __device__ void eliminate_star(const SchurParams& P, const RoundCtx& rc, int vie
 // bounds (b, nb) and walked its fill list into shared memory (`fills`, nfill entries), and guarantees
 // nb + nfill <= W: the raw list always fits, nothing is retried.
 // `slot0` / `nslots`: pool slots reserved for this star by the caller (an upper bound, 2 per possible fill).
-template <int W>
-__device__ void eliminate_star_tile(const SchurParams& P, const RoundCtx& rc, unsigned int idx, int b, int nb,
+template <int W, class PT>
+__device__ void eliminate_star_tile(const PT& P, const RoundCtx& rc, unsigned int idx, int b, int nb,
                                     const uint64_t* fills, int nfill, long long slot0, int nslots, int M,
-                                    LocalStats& ls, PendingPush& pend, LowAppender& la) {
+                                    LocalStats* ls, PendingPush& pend, LowAppender& la) {
     typedef Tile<W> T;
     const int tl = T::tl();
     const bool active = idx != 0xffffffffu;
@@ -392,7 +413,7 @@ __device__ void eliminate_star_tile(const SchurParams& P, const RoundCtx& rc, un
         cross0 = old > M && old - (mult - 1) <= M;
     }
     const bool live = (hmask >> tl) & 1u;
-    const bool full = (P.flags & 1) != 0;
+    const bool full = P.full;
     const bool coarsen = (P.o_v == 2) && !full;
     const int on = coarsen ? 2 : P.o_n;
     uint64_t key = ~0ull, tie = 0;
@@ -495,9 +516,9 @@ __device__ void eliminate_star_tile(const SchurParams& P, const RoundCtx& rc, un
         }
     }
     if (go && tl == 0) {
-        ls.fills += (unsigned long long)(ovf ? 0 : nf);
-        ls.maxstar = max(ls.maxstar, L);
-        ls.raw += (unsigned long long)lraw;
+        ls->fills += (unsigned long long)(ovf ? 0 : nf);
+        ls->maxstar = max(ls->maxstar, L);
+        ls->raw += (unsigned long long)lraw;
         P.state[vb + v] = 2;
         *live_p(P, vb + v) = RLAP_LIVE_DEAD;
     }
@@ -505,17 +526,263 @@ __device__ void eliminate_star_tile(const SchurParams& P, const RoundCtx& rc, un
 }
 
 // ---------------------------------------------------------------------------------------------
+// lane stars: one THREAD per star
+// ---------------------------------------------------------------------------------------------
+// A star with at most LCAP live entries and no multi-edge is gathered, ordered, sampled and pushed by a single lane
+// out of its own shared-memory slot. The register tiles keep 4 (8 lanes) or 2 (16 lanes) dependent chains of memory
+// round trips in flight per warp and spend a warp-wide sorting network on 7..13 entries; here a warp keeps 32 chains
+// in flight and every lane runs a short insertion sort over an almost sorted list. The arithmetic is the keyed
+// specification's to the bit: same fixed point, same tie rules (a star of at most 16 neighbours
+// breaks asc / desc ties by neighbour id), same Philox counters, same IEEE double weight formula.
+// Stars the lane cannot finish alone (a multi-edge, which needs the summed fixed-point weight of the run; two equal
+// 32-bit shuffle keys, which need the full 64-bit key; more entries than announced) are handed to the cooperative
+// path untouched: the lane returns false before it has modified anything.
+constexpr int LCAP = 16;          // entries per lane slot
+constexpr int LANE_NB_MAX = 48;   // longest base row a single lane scans
+
+struct LaneSlot {                 // element e of this lane: A[e * 32], K[e * 32] (conflict free when the lanes of a
+    uint64_t* A;                  // warp touch the same e)
+    uint32_t* K;                  // 32-bit shuffle keys (o_n = random, coarsen), nullptr otherwise
+    __device__ __forceinline__ uint64_t& a(int e) const { return A[e * 32]; }
+    __device__ __forceinline__ uint32_t& k(int e) const { return K[e * 32]; }
+};
+
+// `cross` / `cross_idx`: the neighbour whose live counter this star moved to the segment's level or below (at most
+// one per star: the last one in o_n order, or the contraction target); the caller appends it to the low list with
+// one warp-collective push.
+template <class PT>
+__device__ bool eliminate_star_lane(const PT& P, const RoundCtx& rc, unsigned int idx, int b, int nb,
+                                    long long slot0, int nslots, int M, LaneSlot sl, int& made_out, int& len_out,
+                                    const LowAppender& la, bool& cross, unsigned int& cross_idx) {
+    const int view = (int)(idx / (unsigned)P.n), v = (int)(idx % (unsigned)P.n);
+    const size_t vb = (size_t)view * (size_t)P.n;
+    const uint32_t view_id = P.view_base + (uint32_t)view;
+    int4* pool = P.pool + (size_t)view * (size_t)P.pool_cap;
+    // ---- gather the live entries: base row four at a time (ids and weights, then the dead tests together), then the
+    // fill list with the next hop in flight while the previous entry's neighbour is tested
+    int p = ldcg_i32(head_p(P, idx));
+    int cnt = 0;
+    uint32_t wmaxb = 0;
+    for (int p0 = 0; p0 < nb; p0 += 4) {
+        int u4[4], l4[4];
+        float w4[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const bool in = p0 + k < nb;
+            u4[k] = in ? __ldg(P.col + b + p0 + k) : -1;
+            w4[k] = in ? __ldg(P.w + b + p0 + k) : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) l4[k] = (u4[k] >= 0) ? ldcg_i32(live_p(P, vb + u4[k])) : -1;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (l4[k] >= 0) {
+                if (cnt < LCAP) sl.a(cnt) = pack_a((uint32_t)u4[k], w4[k]);
+                cnt++;
+                wmaxb = max(wmaxb, __float_as_uint(w4[k]));
+            }
+        }
+    }
+    const int nbase = cnt;
+    {
+        int4 pe = make_int4(-1, 0, -1, 0);
+        while (true) {
+            int4 en = make_int4(-1, 0, -1, 0);
+            if (p >= 0) en = __ldcg(pool + p);
+            if (pe.x >= 0 && ldcg_i32(live_p(P, vb + pe.x)) >= 0) {
+                if (cnt < LCAP) sl.a(cnt) = pack_a((uint32_t)pe.x, __int_as_float(pe.y));
+                cnt++;
+                wmaxb = max(wmaxb, (uint32_t)pe.y);
+            }
+            if (p < 0) break;
+            pe = en;
+            p = en.z;
+        }
+    }
+    if (cnt > LCAP || 2 * (cnt - 1) > nslots) return false;   // more live entries than the counter announced: not this path
+    const int L = cnt;
+    // ---- order by neighbour (the base entries are ascending already); a multi-edge sends the star to the cooperative path
+    {
+        bool dup = false;
+        for (int i = (nbase > 1 ? nbase : 1); i < L; i++) {
+            const uint64_t x = sl.a(i);
+            int j = i - 1;
+            while (j >= 0) {
+                const uint64_t y = sl.a(j);
+                if (a_nbr(y) <= a_nbr(x)) { dup |= a_nbr(y) == a_nbr(x); break; }
+                sl.a(j + 1) = y;
+                j--;
+            }
+            sl.a(j + 1) = x;
+        }
+        if (dup) return false;
+    }
+    const bool coarsen = P.o_v == 2;
+    const int on = coarsen ? 2 : P.o_n;
+    const int shift = L > 0 ? star_shift(__uint_as_float(wmaxb), L) : 0;
+    // ---- o_n order: stable insertion sorts, so ties keep the neighbour-id order
+    if (on == 2) {
+        for (int e = 0; e < L; e++) {
+            const uint4 x = philox4x32_10(P.k0, P.k1, (uint32_t)v, a_nbr(sl.a(e)), view_id, TAG_STAR);
+            sl.k(e) = x.z;
+        }
+        bool tie = false;
+        for (int i = 1; i < L; i++) {
+            const uint64_t x = sl.a(i);
+            const uint32_t kx = sl.k(i);
+            int j = i - 1;
+            while (j >= 0) {
+                const uint32_t ky = sl.k(j);
+                if (ky <= kx) { tie |= ky == kx; break; }
+                sl.a(j + 1) = sl.a(j);
+                sl.k(j + 1) = ky;
+                j--;
+            }
+            sl.a(j + 1) = x;
+            sl.k(j + 1) = kx;
+        }
+        if (tie) return false;   // the full key is (z, w) of the Philox block: let the cooperative path compare all 64 bits
+    } else {
+        for (int i = 1; i < L; i++) {
+            const uint64_t x = sl.a(i);
+            const unsigned long long qx = quantize(a_w(x), shift);
+            int j = i - 1;
+            while (j >= 0) {
+                const uint64_t y = sl.a(j);
+                if ((uint32_t)y == (uint32_t)x) break;   // equal weights: equal keys
+                const unsigned long long qy = quantize(a_w(y), shift);
+                if (on == 0 ? !(qx < qy) : !(qx > qy)) break;
+                sl.a(j + 1) = y;
+                j--;
+            }
+            sl.a(j + 1) = x;
+        }
+    }
+    unsigned long long S = 0;
+    for (int e = 0; e < L; e++) S += quantize(a_w(sl.a(e)), shift);
+    const int nf = L > 0 ? L - 1 : 0;
+    const bool ovf = nslots > 0 && slot0 + nslots > P.pool_cap;
+    if (ovf) set_status(P, 5);
+    cross = false;
+    int made = 0;
+    // one fill edge behind: the `next` fields of a fill's two pool entries (the values its list-head exchanges
+    // return) are stored while the next fill is being sampled
+    int4* pp = nullptr;
+    int pj = 0, pk = 0, pn0 = 0, pn1 = 0, pw = 0;
+    auto emit_fill = [&](int j, int k, float w, long long slot) -> bool {
+        if (!(w > 0.f)) {   // underflowed fill: two tombstones, the pool is read linearly at emission
+            pool[slot] = make_int4(-1, 0, -1, -1);
+            pool[slot + 1] = make_int4(-1, 0, -1, -1);
+            return false;
+        }
+        const int s0 = (int)slot, s1 = (int)slot + 1;
+        const int n0 = atomicExch(head_p(P, vb + j), s0);
+        const int n1 = atomicExch(head_p(P, vb + k), s1);
+        if (P.o_v == 0 && ldcg_u8(P.state + vb + j) == 1 && ldcg_u8(P.state + vb + k) == 1) {
+            const int rj = ldcg_i32(P.rank + vb + j), rk = ldcg_i32(P.rank + vb + k);
+            if (rj < rk) atomicAdd(P.blk + vb + k, 1); else atomicAdd(P.blk + vb + j, 1);
+        }
+        if (pp) { pp[0] = make_int4(pk, pw, pn0, pj); pp[1] = make_int4(pj, pw, pn1, pk); }
+        pp = pool + s0; pj = j; pk = k; pn0 = n0; pn1 = n1; pw = __float_as_int(w);
+        return true;
+    };
+    // a neighbour that lost its entry to v and got no fill in return
+    auto lose_one = [&](int u) {
+        const int old = atomicSub(live_p(P, vb + u), 1);
+        if (old > M && old - 1 <= M) la.push_single((unsigned int)(vb + (size_t)u));
+    };
+    if (L > 0 && !ovf) {
+        if (coarsen) {
+            const uint4 x = philox4x32_10(P.k0, P.k1, (uint32_t)v, 0xffffffffu, view_id, TAG_PICK);
+            const unsigned long long u = ((unsigned long long)x.x << 32) | (unsigned long long)x.y;
+            const unsigned long long rr = __umul64hi(u, S);
+            int koff = L - 1;
+            unsigned long long c = 0;
+            for (int k = 0; k < L - 1; k++) {
+                c += quantize(a_w(sl.a(k)), shift);
+                if (c > rr) { koff = k; break; }
+            }
+            const uint64_t ek = sl.a(koff);
+            const double wk = (double)a_w(ek);
+            for (int m = 0; m < L; m++) {
+                if (m == koff) continue;
+                const uint64_t em = sl.a(m);
+                const double wm = (double)a_w(em);
+                const float w = __double2float_rn(__ddiv_rn(__dmul_rn(wk, wm), __dadd_rn(wk, wm)));
+                if (emit_fill((int)a_nbr(em), (int)a_nbr(ek), w, slot0 + 2LL * (m < koff ? m : m - 1))) made++;
+                else lose_one((int)a_nbr(em));
+            }
+            // the contraction target loses its entry to v and gains one per fill
+            if (made != 1) {
+                const int old = atomicAdd(live_p(P, vb + (int)a_nbr(ek)), made - 1);
+                if (made == 0) { cross = old > M && old - 1 <= M; cross_idx = (unsigned int)(vb + (size_t)a_nbr(ek)); }
+            }
+        } else {
+            unsigned long long C = 0;
+            const double Sd = __ull2double_rn(S);
+            for (int j = 0; j < L - 1; j++) {
+                const uint64_t ej = sl.a(j);
+                C += quantize(a_w(ej), shift);
+                const unsigned long long rem = S - C;
+                const uint4 x = philox4x32_10(P.k0, P.k1, (uint32_t)v, a_nbr(ej), view_id, TAG_STAR);
+                const unsigned long long u = ((unsigned long long)x.x << 32) | (unsigned long long)x.y;
+                const unsigned long long rr = C + __umul64hi(u, rem);
+                int koff = L - 1;
+                unsigned long long c = C;
+                for (int k = j + 1; k < L - 1; k++) {
+                    c += quantize(a_w(sl.a(k)), shift);
+                    if (c > rr) { koff = k; break; }
+                }
+                const int kn = (int)a_nbr(sl.a(koff));
+                const float w = __double2float_rn(__ddiv_rn(__dmul_rn((double)a_w(ej), __ull2double_rn(rem)), Sd));
+                if (emit_fill((int)a_nbr(ej), kn, w, slot0 + 2LL * j)) { made++; atomicAdd(live_p(P, vb + kn), 1); }
+                else lose_one((int)a_nbr(ej));
+            }
+            // the last neighbour only loses its entry
+            const int ul = (int)a_nbr(sl.a(L - 1));
+            const int old = atomicSub(live_p(P, vb + ul), 1);
+            cross = old > M && old - 1 <= M;
+            cross_idx = (unsigned int)(vb + (size_t)ul);
+        }
+        if (pp) { pp[0] = make_int4(pk, pw, pn0, pj); pp[1] = make_int4(pj, pw, pn1, pk); }
+        // reserved but unused slots (cannot happen while the live counters are exact): tombstones
+        for (int u = 2 * nf; u < nslots; u++) pool[slot0 + u] = make_int4(-1, 0, -1, -1);
+    } else if (L > 0) {
+        for (int e = 0; e < L; e++) atomicSub(live_p(P, vb + (int)a_nbr(sl.a(e))), 1);   // pool overflow: the run is invalid, keep it going
+    }
+    if (P.o_v == 0) {
+        // pushes and dependency increments are ordered before the decrements
+        __threadfence();
+        for (int e = 0; e < L; e++) {
+            const int u = (int)a_nbr(sl.a(e));
+            if (ldcg_u8(P.state + vb + u) == 1) {
+                const int old = atomicSub(P.blk + vb + u, 1);
+                if (old == 1) {
+                    const int pos = rc.wl_base + atomicAdd(P.ctr + rc.wslot, 1);
+                    P.wl[pos] = (unsigned int)(vb + (size_t)u);
+                }
+            }
+        }
+    }
+    made_out = made;
+    len_out = L;
+    P.state[vb + v] = 2;
+    *live_p(P, vb + v) = RLAP_LIVE_DEAD;
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
 // the persistent elimination kernel
 // ---------------------------------------------------------------------------------------------
 
-constexpr int FCAP = 8;   // fill entries per item that the chunk prologue stages in shared memory
+constexpr int FCAP = 16;  // fill entries per item that the chunk prologue stages in shared memory (32 x FCAP words = the lane slots)
 
 // Run one tier: the items whose bit is set in `mask` (lane i holds item i of the warp's chunk) are handed
 // to the 32 / W tiles of the warp, 32 / W at a time.
-template <int W>
-__device__ void run_tier(const SchurParams& P, const RoundCtx& rc, unsigned mask, unsigned int my_idx, int my_b,
+template <int W, class PT>
+__device__ void run_tier(const PT& P, const RoundCtx& rc, unsigned mask, unsigned int my_idx, int my_b,
                          int my_nb, int my_nfill, const uint64_t* fbuf, long long my_slot0, int my_nslots, int my_M,
-                         LocalStats& ls, PendingPush& pend, LowAppender& la) {
+                         LocalStats* ls, PendingPush& pend, LowAppender& la) {
     constexpr int TPW = 32 / W;
     const int lane = threadIdx.x & 31;
     const int tile = lane / W;
@@ -542,53 +809,95 @@ __device__ void run_tier(const SchurParams& P, const RoundCtx& rc, unsigned mask
     }
 }
 
-// process work-list items [start, end): a warp takes a chunk of up to 32 items and serves them tier by
-// tier (8-, 16-, 32-lane register tiles, then the shared-memory path); big stars go to the block phase
-__device__ void run_warp_items(const SchurParams& P, const RoundCtx& rc, uint64_t* smem, CtaScratch* cs, int* next,
-                               int start, int end, LocalStats& ls, LowAppender& la) {
-    const int gw = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+// shared memory of the elimination phase, per warp: the lane slots (LCAP x 32 entries, plus 32-bit shuffle keys when
+// the neighbour order is random), overlaid by the staging area of the register tiles and the star buffer of the
+// shared-memory path, which run after the lane stars of a chunk
+constexpr int LANE_A_WORDS = LCAP * 32;                       // uint64 per warp
+__host__ __device__ __forceinline__ int warp_region_words(bool need_keys) {
+    return LANE_A_WORDS + (need_keys ? LCAP * 32 / 2 : 0);    // uint64 words: 4 KB (+ 2 KB)
+}
+template <class PT>
+__device__ __forceinline__ bool lane_keys_needed(const PT& P) { return !P.full && (P.o_v == 2 || P.o_n == 2); }
+template <class PT>
+__device__ __forceinline__ StarBuf warp_region_buf(const PT& P, uint64_t* smem) {
+    uint64_t* base = smem + (size_t)(threadIdx.x >> 5) * warp_region_words(lane_keys_needed(P));
+    StarBuf sb;
+    sb.A = base;
+    sb.Q = base + CAP_WARP;
+    sb.K = base + 2 * CAP_WARP;
+    sb.cap = CAP_WARP;
+    return sb;
+}
+
+// process work-list items [start, end): a warp takes a chunk of up to 32 items, one per lane. Stars of at most LCAP
+// live entries are eliminated by their lane alone (eliminate_star_lane); up to 32 raw entries by the warp as a
+// register tile; up to CAP_WARP by the warp in shared memory; big stars go to the block phase.
+template <class PT>
+__device__ void run_warp_items(const PT& P, const RoundCtx& rc, uint64_t* smem, CtaScratch* cs, int* next,
+                               int start, int end, LocalStats* ls, LowAppender& la) {
     const int nw = (int)((gridDim.x * blockDim.x) >> 5);
     const int lane = threadIdx.x & 31;
-    StarBuf sb = warp_buf(smem);
-    uint64_t* fbuf = sb.A;   // 32 x FCAP staged fill entries; the shared-memory path reuses the area afterwards
+    StarBuf sb = warp_region_buf(P, smem);
+    uint64_t* fbuf = sb.A;   // 32 x FCAP staged fill entries of the register tiles; the shared-memory path reuses the area
+    LaneSlot slot;
+    slot.A = sb.A + lane;
+    slot.K = lane_keys_needed(P) ? (uint32_t*)(sb.A + LANE_A_WORDS) + lane : nullptr;
     const int count = end - start;
     if (count <= 0) return;
-    // All warps of the launch (a view group: ~150 warps) fetch chunks of the round's work list from one global cursor,
-    // with a guided size: 1 / (2 x warps) of what is left, at least 4 and at most 32 items. Blocks share their SMs
-    // with the blocks of other groups and run at different speeds; per-block slices left a third of the phase's warp
-    // time waiting for the slowest block (wait timers, profiles/README.md). A stale read of the cursor only changes a
-    // chunk size. flags & 256: static stride, for comparison.
-    const bool dynamic = (P.flags & 256) == 0;
-    int chunk = 32, c0 = 0, cstep = 0, chunk_now = 0;
-    const int my_end = end;
-    if (!dynamic) {
-        chunk = (count + nw - 1) / nw;       // spread small rounds over all warps
-        if (chunk > 32) chunk = 32;
-        c0 = start + gw * chunk; cstep = nw * chunk;
-    }
+    // All warps of the launch (a view group) fetch chunks of the round's work list from one global cursor, with a
+    // guided size: 1 / (2 x warps) of what is left, at least 8 and at most 32 items. A stale read of the cursor only
+    // changes a chunk size.
     (void)next;
-    for (;; c0 += cstep) {
-        if (dynamic) {
-            if (lane == 0) {
-                const int left = count - ldcg_i32(P.ctr + rc.sslot);
-                int c = left / (2 * nw);
-                c = (c + 3) & ~3;
-                c = c < 4 ? 4 : (c > 32 ? 32 : c);
-                c0 = start + atomicAdd(P.ctr + rc.sslot, c);
-                chunk_now = c;
-            }
-            c0 = __shfl_sync(RLAP_FULL_MASK, c0, 0);
-            chunk_now = __shfl_sync(RLAP_FULL_MASK, chunk_now, 0);
+    const bool full = P.full;
+    enum { K_NONE = 0, K_LANE = 1, K_TILE = 2, K_SMEM = 3 };
+    // pool slots are reserved once per chunk and tier: 2 per possible fill (L <= live), one atomic per view present in
+    // the chunk instead of one per star
+    auto reserve = [&](int nslots, int view) -> long long {
+        long long slot0 = 0;
+        int incl = nslots;  // inclusive prefix over the lanes of the chunk
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int t = __shfl_up_sync(RLAP_FULL_MASK, incl, d);
+            if (lane >= d) incl += t;
         }
-        if (c0 >= my_end) break;
-        const int end = my_end;
+        const unsigned need = __ballot_sync(RLAP_FULL_MASK, nslots > 0);
+        if (need) {
+            const int first = __ffs(need) - 1, last = 31 - __clz(need);
+            const int v0 = __shfl_sync(RLAP_FULL_MASK, view, first);
+            const bool same = __all_sync(RLAP_FULL_MASK, nslots == 0 || view == v0);
+            if (same) {
+                const int total = __shfl_sync(RLAP_FULL_MASK, incl, last);
+                unsigned long long b0 = 0;
+                if (lane == first) b0 = atomicAdd(P.pool_cursor + v0, (unsigned long long)total);
+                b0 = __shfl_sync(RLAP_FULL_MASK, b0, first);
+                slot0 = (long long)b0 + incl - nslots;
+            } else if (nslots > 0) {
+                slot0 = (long long)atomicAdd(P.pool_cursor + view, (unsigned long long)nslots);
+            }
+        }
+        return slot0;
+    };
+    while (true) {
+        int c0 = 0, chunk_now = 0;
+        if (lane == 0) {
+            const int left = count - ldcg_i32(P.ctr + rc.sslot);
+            int c = left / (2 * nw);
+            c = (c + 7) & ~7;
+            c = c < 8 ? 8 : (c > 32 ? 32 : c);
+            c0 = start + atomicAdd(P.ctr + rc.sslot, c);
+            chunk_now = c;
+        }
+        c0 = __shfl_sync(RLAP_FULL_MASK, c0, 0);
+        chunk_now = __shfl_sync(RLAP_FULL_MASK, chunk_now, 0);
+        if (c0 >= end) break;
         const int it = c0 + lane;
         unsigned int idx = 0xffffffffu;
-        int lv = -1, cls = -1, b = 0, nb = 0, nfill = 0, M = -1;
-        __syncwarp();   // the previous chunk is done with the staging buffer
-        if (lane < (dynamic ? chunk_now : chunk) && it < end) {
+        int lv = -1, kind = K_NONE, b = 0, nb = 0, nfill = 0, M = -1, view = -1;
+        __syncwarp();   // the previous chunk is done with the shared-memory region
+        if (lane < chunk_now && it < end) {
             idx = __ldcg(P.wl + it);
-            const int view = (int)(idx / (unsigned)P.n), v = (int)(idx % (unsigned)P.n);
+            view = (int)(idx / (unsigned)P.n);
+            const int v = (int)(idx % (unsigned)P.n);
             bool skip = false;
             if (P.o_v != 0) {  // truncated final round of a graph: only the highest ids go
                 size_t seg = (size_t)view * P.G + graph_of(P, v);
@@ -599,22 +908,12 @@ __device__ void run_warp_items(const SchurParams& P, const RoundCtx& rc, uint64_
                 lv = ldcg_i32(live_p(P, idx));
                 b = __ldg(P.ptr + v);
                 nb = __ldg(P.ptr + v + 1) - b;
-                if (lv <= CAP_WARP) {
-                    // every lane walks the fill list of its own item (32 chains in flight) into the staging buffer;
-                    // with the CSR bounds this gives the exact raw length, i.e. the tile width that holds the star
-                    const int4* pool = P.pool + (size_t)view * (size_t)P.pool_cap;
-                    int p = ldcg_i32(head_p(P, idx));
-                    while (p >= 0 && nfill < FCAP) {
-                        const int4 en = __ldcg(pool + p);
-                        fbuf[lane * FCAP + nfill] = pack_a((uint32_t)en.x, __int_as_float(en.y));
-                        nfill++;
-                        p = en.z;
-                    }
-                    cls = (p >= 0 || nb + nfill > 32) ? 33 : nb + nfill;   // 33: the shared-memory path gathers it itself
-                    if (P.flags & 64) cls = 33;   // debug: no register tiles
-                } else {
-                    cls = lv;
-                }
+                if (lv > CAP_WARP) kind = K_NONE;          // deferred to the block phase below
+                else if (!full && lv <= LCAP && nb <= LANE_NB_MAX) kind = K_LANE;
+                else if (lv <= 32 && nb <= 32) kind = K_TILE;   // if its fill list is short enough, see below
+                else kind = K_SMEM;
+            } else {
+                idx = 0xffffffffu;
             }
         }
         __syncwarp();
@@ -622,47 +921,61 @@ __device__ void run_warp_items(const SchurParams& P, const RoundCtx& rc, uint64_
             int pos = rc.dl_base + atomicAdd(P.ctr + rc.dslot, 1);
             P.dl[pos] = idx;
         }
-        unsigned m8 = __ballot_sync(RLAP_FULL_MASK, cls >= 0 && cls <= 8);
-        unsigned m16 = __ballot_sync(RLAP_FULL_MASK, cls > 8 && cls <= 16);
-        unsigned m32 = __ballot_sync(RLAP_FULL_MASK, cls > 16 && cls <= 32);
-        unsigned msm = __ballot_sync(RLAP_FULL_MASK, cls > 32 && lv <= CAP_WARP);
-        // pool slots for the register tiers are reserved once per chunk: 2 per possible fill (L <= live), one
-        // atomic per view present in the chunk instead of one per star
-        const bool full = (P.flags & 1) != 0;
-        int nslots = 0;
-        if (lv >= 2 && cls <= 32) nslots = full ? lv * (lv - 1) : 2 * (lv - 1);
-        long long slot0 = 0;
-        {
-            const int view = (idx == 0xffffffffu) ? -1 : (int)(idx / (unsigned)P.n);
-            int incl = nslots;  // inclusive prefix over the lanes of the chunk
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                int t = __shfl_up_sync(RLAP_FULL_MASK, incl, d);
-                if (lane >= d) incl += t;
-            }
-            const unsigned need = __ballot_sync(RLAP_FULL_MASK, nslots > 0);
-            if (need) {
-                const int first = __ffs(need) - 1, last = 31 - __clz(need);
-                const int v0 = __shfl_sync(RLAP_FULL_MASK, view, first);
-                const bool same = __all_sync(RLAP_FULL_MASK, nslots == 0 || view == v0);
-                if (same) {
-                    const int total = __shfl_sync(RLAP_FULL_MASK, incl, last);
-                    unsigned long long b0 = 0;
-                    if (lane == first) b0 = atomicAdd(P.pool_cursor + v0, (unsigned long long)total);
-                    b0 = __shfl_sync(RLAP_FULL_MASK, b0, first);
-                    slot0 = (long long)b0 + incl - nslots;
-                } else if (nslots > 0) {
-                    slot0 = (long long)atomicAdd(P.pool_cursor + view, (unsigned long long)nslots);
+        // ---- lane stars
+        if (__any_sync(RLAP_FULL_MASK, kind == K_LANE)) {
+            const int nslots = (kind == K_LANE && lv >= 2) ? 2 * (lv - 1) : 0;
+            const long long slot0 = reserve(nslots, view);
+            bool cross = false;
+            unsigned int cross_idx = 0;
+            int made = 0, len = 0;
+            if (kind == K_LANE) {
+                if (eliminate_star_lane(P, rc, idx, b, nb, slot0, nslots, M, slot, made, len, la, cross, cross_idx)) {
+                    kind = K_NONE;
+                } else {
+                    // handed to the cooperative path, which reserves its own slots: these stay tombstones
+                    for (int u = 0; u < nslots; u++) {
+                        if (slot0 + u < P.pool_cap) (P.pool + (size_t)view * (size_t)P.pool_cap)[slot0 + u] = make_int4(-1, 0, -1, -1);
+                    }
+                    kind = K_SMEM;
                 }
             }
+            __syncwarp();
+            la.push(cross, cross_idx);
+            made = __reduce_add_sync(RLAP_FULL_MASK, made);
+            const int lsum = __reduce_add_sync(RLAP_FULL_MASK, len), lmax = __reduce_max_sync(RLAP_FULL_MASK, len);
+            if (lane == 0) {
+                ls->fills += (unsigned long long)made;
+                ls->raw += (unsigned long long)lsum;
+                ls->maxstar = max(ls->maxstar, lmax);
+            }
         }
-        PendingPush pend;
-        run_tier<8>(P, rc, m8, idx, b, nb, nfill, fbuf, slot0, nslots, M, ls, pend, la);
-        run_tier<16>(P, rc, m16, idx, b, nb, nfill, fbuf, slot0, nslots, M, ls, pend, la);
-        run_tier<32>(P, rc, m32, idx, b, nb, nfill, fbuf, slot0, nslots, M, ls, pend, la);
-        pend.flush(la);
-        __syncwarp();
-        if (lane == 0) ls.nsm += (unsigned)__popc(msm);
+        // ---- register tiles (17 .. 32 raw entries): every lane first walks the fill list of its own item (32 chains
+        // in flight) into the staging buffer; with the CSR bounds this gives the exact raw length
+        if (__any_sync(RLAP_FULL_MASK, kind == K_TILE)) {
+            if (kind == K_TILE) {
+                const int4* pool = P.pool + (size_t)view * (size_t)P.pool_cap;
+                int p = ldcg_i32(head_p(P, idx));
+                while (p >= 0 && nfill < FCAP) {
+                    const int4 en = __ldcg(pool + p);
+                    fbuf[lane * FCAP + nfill] = pack_a((uint32_t)en.x, __int_as_float(en.y));
+                    nfill++;
+                    p = en.z;
+                }
+                if (p >= 0 || nb + nfill > 32) kind = K_SMEM;   // the shared-memory path gathers it itself
+            }
+            __syncwarp();
+            int nslots = 0;
+            if (kind == K_TILE && lv >= 2) nslots = full ? lv * (lv - 1) : 2 * (lv - 1);
+            const long long slot0 = reserve(nslots, view);
+            const unsigned m32 = __ballot_sync(RLAP_FULL_MASK, kind == K_TILE);
+            PendingPush pend;
+            run_tier<32>(P, rc, m32, idx, b, nb, nfill, fbuf, slot0, nslots, M, ls, pend, la);
+            pend.flush(la);
+            __syncwarp();
+        }
+        // ---- shared-memory path
+        unsigned msm = __ballot_sync(RLAP_FULL_MASK, kind == K_SMEM);
+        if (lane == 0) ls->nsm += (unsigned)__popc(msm);
         while (msm) {
             int k = __ffs(msm) - 1;
             msm &= msm - 1;
@@ -674,8 +987,9 @@ __device__ void run_warp_items(const SchurParams& P, const RoundCtx& rc, uint64_
 
 // deferred items [start, end): one block per item in shared memory; stars beyond CAP_CTA go to the
 // NSLOT blocks that own a global scratch slot
-__device__ void run_block_items(const SchurParams& P, const RoundCtx& rc, uint64_t* smem, CtaScratch* cs, int start,
-                                int end, LocalStats& ls, LowAppender& la) {
+template <class PT>
+__device__ void run_block_items(const PT& P, const RoundCtx& rc, uint64_t* smem, CtaScratch* cs, int start,
+                                int end, LocalStats* ls, LowAppender& la) {
     for (int it = start + (int)blockIdx.x; it < end; it += (int)gridDim.x) {
         unsigned int idx = __ldcg(P.dl + it);
         int view = (int)(idx / (unsigned)P.n), v = (int)(idx % (unsigned)P.n);
@@ -696,11 +1010,13 @@ __device__ void run_block_items(const SchurParams& P, const RoundCtx& rc, uint64
     }
 }
 
-__global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
+template <int OV, int ON, bool FULL>
+__global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(const __grid_constant__ ModeParams<OV, ON, FULL> P) {
     extern __shared__ __align__(16) uint64_t smem[];
     __shared__ CtaScratch cs;
     __shared__ int s_next, s_nsel;
     __shared__ unsigned int s_lowbuf[WARPS_PER_BLOCK][LOWBUF];
+    __shared__ LocalStats s_stats[WARPS_PER_BLOCK];
     cg::grid_group grid = cg::this_grid();
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long nthr = (long long)gridDim.x * blockDim.x;
@@ -745,45 +1061,66 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
 
     // phase timing (block 0, thread 0; nanoseconds between grid barriers, waits included)
     unsigned long long tmark = 0;
+#ifdef RLAP_DEBUG
+    unsigned int rt[6] = {0, 0, 0, 0, 0, 0};   // this round's phase times (ns), printed with flags & 512
+#endif
     auto lap = [&](int slot) {
         if (tid == 0) {
             unsigned long long now;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
             if (slot >= 0) P.stats[slot] += now - tmark;
+#ifdef RLAP_DEBUG
+            if (slot >= ST_T_INIT) rt[slot - ST_T_INIT] += (unsigned int)(now - tmark);
+#endif
             tmark = now;
         }
     };
     lap(-1);
-    // grid barrier that ends a phase; with flags & 128 every warp also records how long it waited there
+    // grid barrier that ends a phase; a -DRLAP_DEBUG build with flags & 128 also records how long every warp waited there
+#ifdef RLAP_DEBUG
     const bool wait_timers = (P.flags & 128) != 0;
+#endif
     auto gsync = [&](int slot) {
+#ifdef RLAP_DEBUG
         unsigned long long t0 = 0;
         if (wait_timers && (threadIdx.x & 31) == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+#endif
         grid.sync();
+#ifdef RLAP_DEBUG
         if (wait_timers && (threadIdx.x & 31) == 0) {
             unsigned long long t1;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
             atomicAdd(P.stats + ST_W_INIT + (slot - ST_T_INIT), t1 - t0);
         }
+#endif
         lap(slot);
     };
-    // debug (flags & 512): thread 0 of block 0 times the parts of phase B
+    // -DRLAP_DEBUG with flags & 512: thread 0 of block 0 times the parts of phase B
+#ifdef RLAP_DEBUG
     unsigned long long dmark = 0;
+#endif
     auto dlap = [&](int slot) {
+#ifdef RLAP_DEBUG
         if ((P.flags & 512) && tid == 0) {
             unsigned long long now;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
             if (slot >= 0) P.stats[ST_DBG + slot] += now - dmark;
             dmark = now;
         }
+#else
+        (void)slot;
+#endif
     };
     int wl_start = 0;   // first unconsumed work-list item
     int dl_start = 0;
     int rounds = 0;
     RoundCtx rc;
-    LocalStats ls;
+    LocalStats* ls = s_stats + (threadIdx.x >> 5);
+    if ((threadIdx.x & 31) == 0) { ls->fills = 0; ls->raw = 0; ls->maxstar = 0; ls->nsm = 0; }
+    __syncwarp();
     LowAppender la;
     la.buf = s_lowbuf[threadIdx.x >> 5];
+    la.P = &P;
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
     const unsigned uVN = (unsigned)VN, un = (unsigned)P.n;
@@ -874,10 +1211,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
         while (true) {
             const int par = rounds & 1;
             const unsigned int* low_in = P.low + (size_t)par * (size_t)P.low_cap;
-            la.dst = P.low + (size_t)(par ^ 1) * (size_t)P.low_cap;
-            la.cap = P.low_cap;
-            la.tail = P.ctr + CTR_LOW0 + (par ^ 1);
-            la.ovf = P.ctr + CTR_LOWOVF0 + (par ^ 1);
+            la.par = par ^ 1;
             long long n_in = ldcg_i32(P.ctr + CTR_LOW0 + par);
             if (n_in > P.low_cap) n_in = P.low_cap;
             if (ldcg_i32(P.ctr + CTR_LOWOVF0 + par)) n_in = 0;   // entries were lost: every segment rescans
@@ -923,6 +1257,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
                 if (any && lane == 0) P.ctr[CTR_ACTIVE0 + par] = 1;
             }
             gsync(ST_T_A);
+#ifdef RLAP_DEBUG
             if ((P.flags & 512) && tid == 0) {   // debug: list size and number of rescanning segments per round
                 int ns = 0, mn = INF;
                 for (long long q = 0; q < VG; q++) {
@@ -932,6 +1267,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
                 printf("round %d: low list %lld entries, %d of %lld segments rescan, min list key %d, lvl[0] %d rem[0] %d\n",
                        rounds, n_in, ns, VG, mn, P.lvl[0], P.rem[0]);
             }
+#endif
             // ---- phase A2: segments with nothing in play on the list scan all their vertices for the minimum key
             {
                 int* smin = (int*)smem;         // [VG] block-level minima
@@ -1329,6 +1665,9 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
             }
             // phase D: eliminate
             int wl_end = wl_start + ldcg_i32(P.ctr + rc.wslot);
+#ifdef RLAP_DEBUG
+            const int items_dbg = wl_end - wl_start;
+#endif
             run_warp_items(P, rc, smem, &cs, &s_next, wl_start, wl_end, ls, la);
             wl_start = wl_end;
             la.flush();
@@ -1340,15 +1679,22 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(SchurParams P) {
                 la.flush();
                 gsync(ST_T_D2);
             }
+#ifdef RLAP_DEBUG
+            if ((P.flags & 512) && tid == 0 && P.view_base == 0) {
+                printf("round %d items %d low_in %lld | A %u B %u C %u D1 %u D2 %u ns\n", rounds, items_dbg, n_in, rt[1], rt[2], rt[3], rt[4], rt[5]);
+                for (int q = 0; q < 6; q++) rt[q] = 0;
+            }
+#endif
             rounds++;
         }
     }
     if (tid == 0) P.ctr[CTR_ROUNDS] = rounds;
-    if (ls.raw | ls.fills) {
-        atomicAdd(P.stats + ST_FILLS, ls.fills);
-        atomicAdd(P.stats + ST_RAW, ls.raw);
-        atomicMax(P.stats + ST_MAXSTAR, (unsigned long long)ls.maxstar);
-        if (ls.nsm) atomicAdd(P.stats + ST_DEFERRED, (unsigned long long)ls.nsm);
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0 && (ls->raw | ls->fills)) {
+        atomicAdd(P.stats + ST_FILLS, ls->fills);
+        atomicAdd(P.stats + ST_RAW, ls->raw);
+        atomicMax(P.stats + ST_MAXSTAR, (unsigned long long)ls->maxstar);
+        if (ls->nsm) atomicAdd(P.stats + ST_DEFERRED, (unsigned long long)ls->nsm);
     }
 }
 
@@ -1376,7 +1722,13 @@ __global__ void k_setup_graphs(int n, int G, const int* gptr, const long long* n
 // ---------------------------------------------------------------------------------------------
 // host-side launchers (called from api.cu)
 // ---------------------------------------------------------------------------------------------
-static const size_t kSmemBytes = (size_t)3 * CAP_CTA * sizeof(uint64_t);
+// dynamic shared memory of k_eliminate: the block-level star buffer (3 x CAP_CTA words) or the per-warp regions of the
+// elimination phase, whichever is larger
+static size_t eliminate_smem_bytes(bool need_keys) {
+    const size_t cta = (size_t)3 * CAP_CTA * sizeof(uint64_t);
+    const size_t warps = (size_t)WARPS_PER_BLOCK * (size_t)warp_region_words(need_keys) * sizeof(uint64_t);
+    return cta > warps ? cta : warps;
+}
 
 cudaError_t launch_setup_graphs(int n, int G, const int* gptr, const long long* num_remove, int* gid, int* teff,
                                 cudaStream_t stream) {
@@ -1387,20 +1739,59 @@ cudaError_t launch_setup_graphs(int n, int G, const int* gptr, const long long* 
     return cudaGetLastError();
 }
 
-cudaError_t eliminate_grid(int* blocks_out) {
-    static int cached = 0;
-    if (!cached) {
-        cudaError_t e = cudaFuncSetAttribute(k_eliminate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
-        if (e != cudaSuccess) return e;
-        int dev = 0, sms = 0, occ = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_eliminate, BLOCK_THREADS, kSmemBytes);
-        if (e != cudaSuccess) return e;
-        if (occ < 1) return cudaErrorLaunchOutOfResources;
-        cached = sms * occ;
+// One instantiation of k_eliminate per mode. Coarsening fixes the neighbour order (shuffle, preconditioner.cc:831) and
+// the full-clique test mode ignores it, so nine kernels cover every (o_v, o_n, flags) combination.
+constexpr int N_MODES = 9;
+static int mode_index(int o_v, int o_n, bool full) {
+    if (full) return o_v == 0 ? 7 : 8;
+    if (o_v == 2) return 6;
+    return o_v * 3 + o_n;
+}
+static bool mode_needs_keys(int m) { return m == 2 || m == 5 || m == 6; }
+static const void* mode_kernel(int m) {
+    switch (m) {
+        case 0: return (const void*)k_eliminate<0, 0, false>;
+        case 1: return (const void*)k_eliminate<0, 1, false>;
+        case 2: return (const void*)k_eliminate<0, 2, false>;
+        case 3: return (const void*)k_eliminate<1, 0, false>;
+        case 4: return (const void*)k_eliminate<1, 1, false>;
+        case 5: return (const void*)k_eliminate<1, 2, false>;
+        case 6: return (const void*)k_eliminate<2, 2, false>;
+        case 7: return (const void*)k_eliminate<0, 0, true>;
+        default: return (const void*)k_eliminate<1, 0, true>;
     }
-    *blocks_out = cached;
+}
+
+// Function attributes and occupancy are per device: one cached record per device ordinal, filled under a lock.
+constexpr int MAX_DEVICES = 64;
+struct DeviceInfo { bool ready = false; int blocks = 0; };
+static DeviceInfo g_dev[MAX_DEVICES];
+static std::mutex g_dev_mutex;
+
+cudaError_t eliminate_grid(int* blocks_out) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= MAX_DEVICES) return cudaErrorInvalidDevice;
+    std::lock_guard<std::mutex> lk(g_dev_mutex);
+    DeviceInfo& d = g_dev[dev];
+    if (!d.ready) {
+        int sms = 0, occ_min = 1 << 30;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        for (int m = 0; m < N_MODES; m++) {
+            const size_t smem = eliminate_smem_bytes(mode_needs_keys(m));
+            e = cudaFuncSetAttribute(mode_kernel(m), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            int occ = 0;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mode_kernel(m), BLOCK_THREADS, smem);
+            if (e != cudaSuccess) return e;
+            occ_min = occ < occ_min ? occ : occ_min;
+        }
+        if (occ_min < 1) return cudaErrorLaunchOutOfResources;
+        d.blocks = sms * occ_min;   // one grid size for every mode: the view groups of a call partition it
+        d.ready = true;
+    }
+    *blocks_out = d.blocks;
     return cudaSuccess;
 }
 
@@ -1411,7 +1802,9 @@ cudaError_t launch_eliminate(const SchurParams& P, cudaStream_t stream, int bloc
     if (blocks_req > 0 && blocks_req < blocks) blocks = blocks_req;
     SchurParams Pc = P;
     void* args[] = {(void*)&Pc};
-    return cudaLaunchCooperativeKernel((void*)k_eliminate, dim3(blocks), dim3(BLOCK_THREADS), args, kSmemBytes, stream);
+    const int m = mode_index(P.o_v, P.o_n, (P.flags & 1) != 0);
+    return cudaLaunchCooperativeKernel(mode_kernel(m), dim3(blocks), dim3(BLOCK_THREADS), args,
+                                       eliminate_smem_bytes(mode_needs_keys(m)), stream);
 }
 
 // fold the control blocks of the view groups into the caller-visible one: first error, largest round count,

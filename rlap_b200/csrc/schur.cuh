@@ -108,6 +108,20 @@ struct SchurParams {
 };
 
 constexpr int RLAP_LIVE_DEAD = -0x40000000;
+
+// "first call on this device" latch for per-device set-up (function attributes are per device, and a process may use
+// several devices from several threads)
+struct PerDeviceOnce {
+    unsigned long long done[4] = {0, 0, 0, 0};   // 256 device ordinals
+    // returns true exactly once per device ordinal; callers serialise through their own lock
+    bool first(int dev) {
+        if (dev < 0 || dev >= 256) return true;
+        const unsigned long long bit = 1ull << (dev & 63);
+        if (done[dev >> 6] & bit) return false;
+        done[dev >> 6] |= bit;
+        return true;
+    }
+};
 __host__ __device__ __forceinline__ int* live_p(const SchurParams& P, size_t i) { return P.lh + 2 * i; }
 __host__ __device__ __forceinline__ int* head_p(const SchurParams& P, size_t i) { return P.lh + 2 * i + 1; }
 

@@ -24,6 +24,7 @@ _O_N = ["asc", "desc", "random"]
 
 _seed_counter = itertools.count()
 _base_seed = None
+_DEBUG_FLAGS = 0   # profiling bits (128: barrier wait timers, 512: per-round prints); only a -DRLAP_DEBUG build of the library reads them
 
 
 def manual_seed(seed: int) -> None:
@@ -109,7 +110,8 @@ def prepare(edge_index: Tensor, edge_weights: Optional[Tensor], num_nodes: int,
 
 def schur_views(graph: Graph, num_remove, o_v: str, o_n: str, num_views: int = 1, seed: Optional[int] = None,
                 view_base: int = 0, full_clique: bool = False, shared_order: bool = False, dtype=torch.float64,
-                pool_cap: int = 0, scratch_cap: int = 0, return_stats: bool = False, colptr: bool = False):
+                pool_cap: int = 0, scratch_cap: int = 0, return_stats: bool = False, colptr: bool = False,
+                check_live: bool = False):
     """num_views independent randomized Schur-complement views of `graph`.
 
     Returns (edge_info, view_ptr): edge_info is [sum E'_v, 3] (row, col, weight) of `dtype`
@@ -128,7 +130,8 @@ def schur_views(graph: Graph, num_remove, o_v: str, o_n: str, num_views: int = 1
     if seed is None:
         seed = _next_seed()
     flags = (_native.FLAG_FULL_CLIQUE if full_clique else 0) | (_native.FLAG_SHARED_ORDER if shared_order else 0)
-    flags |= int(__import__('os').environ.get('RLAP_DEBUG_FLAGS', '0'))
+    flags |= _native.FLAG_CHECK_LIVE if check_live else 0
+    flags |= _DEBUG_FLAGS
     V = int(num_views)
     if full_clique:  # test mode: cliques instead of trees, multi-edges pile up until a vertex goes
         pool_cap = pool_cap or 8 * graph.nnz + 4096
@@ -149,6 +152,10 @@ def schur_views(graph: Graph, num_remove, o_v: str, o_n: str, num_views: int = 1
                                         stream)
             if st == _native.RLAP_ERR_POOL_OVERFLOW:
                 pool_cap = 2 * int(stats[6])
+                del ws
+                continue
+            if st == _native.RLAP_ERR_STAR_TOO_LARGE and scratch_cap < graph.nnz + 1:
+                scratch_cap = graph.nnz + 1      # a star never holds more entries than the graph
                 del ws
                 continue
             _native.check(st, "schur_eliminate")
@@ -176,6 +183,8 @@ def schur_views(graph: Graph, num_remove, o_v: str, o_n: str, num_views: int = 1
             out = o64[:total]
             if dtype != torch.float64:
                 out = out.to(dtype)
+        # the library forgets the workspace before its memory goes back to the allocator
+        L.rlap_schur_release(ws.data_ptr())
     if return_stats:
         names = ["rounds", "fills", "pool_used_max", "max_star", "raw_entries_read", "rows", "pool_cap", "elim_us",
                  "emit_count_us", "t_init_us", "t_phaseA_us", "t_phaseB_us", "t_phaseC_us", "t_elim_warp_us",

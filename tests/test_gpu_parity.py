@@ -173,17 +173,17 @@ def test_chained_views_extreme_dynamic_range(oracle_port, o_n):
             w, nn = w0, len(nodes)
 
 
-def test_live_counters_are_exact(monkeypatch):
+def test_live_counters_are_exact():
     """compute-sanitizer is closed on this pool, so the library carries its own consistency check
-    (RLAP_DEBUG_CHECK=1): after the elimination, the number of live entries the emission finds for every surviving
+    (RLAP_FLAG_CHECK_LIVE): after the elimination, the number of live entries the emission finds for every surviving
     vertex must equal the live counter the elimination maintained (a mismatch means a lost or phantom entry)."""
     import rlap_b200
-    monkeypatch.setenv("RLAP_DEBUG_CHECK", "1")
     for name, ei, n, gptr, t in util.small_cases():
         for w in (None, util.sym_weights(ei, 1e-6, 10.0)):
             g = _gpu_graph(ei, w, n, gptr)
             for o_v, o_n in util.COMBOS:
-                _, _, st = rlap_b200.schur_views(g, t, o_v, o_n, num_views=4, seed=3, dtype=None, return_stats=True)
+                _, _, st = rlap_b200.schur_views(g, t, o_v, o_n, num_views=4, seed=3, dtype=None, return_stats=True,
+                                                 check_live=True)
                 assert st["check_mismatches"] == 0, (name, o_v, o_n)
 
 
