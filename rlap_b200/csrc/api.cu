@@ -21,7 +21,8 @@ namespace rlap {
 cudaError_t launch_setup_graphs(int n, int G, const int* gptr, const long long* num_remove, int* gid, int* teff,
                                 cudaStream_t stream);
 cudaError_t eliminate_grid(int* blocks_out);
-cudaError_t launch_eliminate(const SchurParams& P, cudaStream_t stream, int blocks_req);
+cudaError_t launch_eliminate(const SchurParams* groups_dev, const int* block_group_dev, int blocks, int o_v, int o_n,
+                             int flags, cudaStream_t stream);
 cudaError_t launch_emit_colptr(const SchurParams& P, int* colptr, cudaStream_t stream);
 cudaError_t launch_combine_groups(int K, const int* gctr, const unsigned long long* gstats, int* ctr,
                                   unsigned long long* stats, cudaStream_t stream);
@@ -66,13 +67,13 @@ struct Mailbox {
 
 // Streams, events and the mailbox belong to the device that was current when they were created: one set per
 // (host thread, device), created on first use on that device.
-constexpr int MAX_GROUPS = 64;
+constexpr int MAX_GROUPS = 1024;   // view groups of one call: at most one per block of the launch
 struct ThreadDevice {
     Mailbox mail;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
-    cudaStream_t gs[MAX_GROUPS] = {nullptr};
-    cudaEvent_t gev[MAX_GROUPS + 1] = {nullptr};
     std::vector<int> gp;
+    std::vector<SchurParams> groups;   // host copy of the parameter blocks of the view groups
+    std::vector<int> block_group;
 };
 static ThreadDevice* thread_device() {
     static thread_local std::unordered_map<int, ThreadDevice*> per_dev;
@@ -246,13 +247,17 @@ struct SchurLayout {
     long long G, V, pool_cap, scratch_cap;
     int* gctr;                 // [MAX_GROUPS][CTR_COUNT] control blocks of the view groups
     unsigned long long* gstats; // [MAX_GROUPS][ST_COUNT]
-    uint64_t* gscratch;        // [MAX_GROUPS] scratch slots
+    uint64_t* gscratch;        // one scratch slot per block that may own one (NSLOT per group at most)
+    SchurParams* gparams;      // [MAX_GROUPS] device copies of the groups' parameter blocks
+    int* block_group;          // [MAX_GROUPS] group of every block of the launch
 };
 
-// The views of one call are eliminated by up to MAX_GROUPS concurrent cooperative launches of k_eliminate, each on its
-// own share of the SMs and with its own grid barrier: views are independent, and a barrier over all of them makes
-// every phase of every view wait for the slowest chain of any view (45 % of the warp time in the single-launch
-// profile, profiles/README.md).
+// The views of one call are eliminated by ONE cooperative launch of k_eliminate whose blocks are partitioned into view
+// groups, each with its own share of the views, its own lists and counters and its own barrier: views are
+// independent, and a barrier over all of them makes every phase of every view wait for the slowest chain of any view
+// (45 % of the warp time in the single-barrier profile, profiles/README.md). A group of one block has no global
+// barrier at all.
+constexpr int MAX_SCRATCH_SLOTS = 512;   // >= blocks of a launch (2 per SM)
 static long long default_pool_cap(long long nnz) { return 2 * nnz + 4096; }
 static long long default_scratch_cap(long long n) {
     long long c = n < 65536 ? n : 65536;
@@ -278,6 +283,8 @@ static SchurLayout schur_layout(long long n, long long nnz, long long G, long lo
     P.stats = c.take<unsigned long long>(ST_COUNT);
     L.gctr = c.take<int>((size_t)MAX_GROUPS * CTR_COUNT);
     L.gstats = c.take<unsigned long long>((size_t)MAX_GROUPS * ST_COUNT);
+    L.gparams = c.take<SchurParams>((size_t)MAX_GROUPS);
+    L.block_group = c.take<int>((size_t)MAX_GROUPS);
     L.total_dev = c.take<long long>(1);
     L.viewptr_dev = c.take<long long>((size_t)V + 1);
     L.gptr_dev = c.take<int>((size_t)G + 1);
@@ -312,8 +319,9 @@ static SchurLayout schur_layout(long long n, long long nnz, long long G, long lo
     P.low_cap = (long long)(2 * VN + 64);
     P.low = c.take<unsigned int>(4 * VN + 128 * (size_t)MAX_GROUPS);
     {
-        const long long groups = V < MAX_GROUPS ? V : MAX_GROUPS;
-        P.scratch = c.take<uint64_t>((size_t)groups * NSLOT * 3 * (size_t)scratch_cap);
+        // a group's first min(NSLOT, blocks of the group) blocks own a slot each: never more slots than blocks
+        const long long slots = V * NSLOT < MAX_SCRATCH_SLOTS ? V * NSLOT : MAX_SCRATCH_SLOTS;
+        P.scratch = c.take<uint64_t>((size_t)slots * 3 * (size_t)scratch_cap);
         L.gscratch = P.scratch;
     }
     P.scratch_cap = (int)scratch_cap;
@@ -399,59 +407,58 @@ int rlap_schur_eliminate(int64_t n, int64_t nnz, const int32_t* csr_ptr, const i
     if (!ev[0]) for (int i = 0; i < 3; i++) CK(cudaEventCreate(&ev[i]));
     CK(cudaEventRecord(ev[0], stream));
     {
-        // view groups: K concurrent cooperative launches, each on blocks / K blocks
+        // view groups: K groups share the blocks of one cooperative launch
         int blocks = 0;
         CK(eliminate_grid(&blocks));
-        long long K = n_views / ((n_views + 31) / 32);   // at most 32 groups (about 9 blocks each), equal shares of views
+        if (blocks > MAX_GROUPS) blocks = MAX_GROUPS;
+        if (blocks > MAX_SCRATCH_SLOTS) blocks = MAX_SCRATCH_SLOTS;
+        // every view its own group while there are at least two blocks per view; with more views than that, one
+        // block per group and the views dealt out evenly
+        long long K = n_views;
+        if (K > blocks / 2) K = n_views >= blocks ? blocks : blocks / 2;
 #ifdef RLAP_DEBUG
         if (const char* env = getenv("RLAP_GROUPS")) { K = atoll(env); }
 #endif
         if (K > n_views) K = n_views;
-        if (K > MAX_GROUPS) K = MAX_GROUPS;
-        if (K > blocks / 2) K = blocks / 2;
+        if (K > blocks) K = blocks;
         if (K < 1) K = 1;
-        if (K == 1) {
-            CK(launch_eliminate(P, stream, 0));
-        } else {
-            cudaStream_t* gs = td->gs;
-            cudaEvent_t* gev = td->gev;
-            for (long long g = 0; g < K; g++) {
-                if (!gs[g]) CK(cudaStreamCreateWithFlags(&gs[g], cudaStreamNonBlocking));
-                if (!gev[g]) CK(cudaEventCreateWithFlags(&gev[g], cudaEventDisableTiming));
-            }
-            if (!gev[MAX_GROUPS]) CK(cudaEventCreateWithFlags(&gev[MAX_GROUPS], cudaEventDisableTiming));
-            CK(cudaMemsetAsync(L.gctr, 0, sizeof(int) * CTR_COUNT * (size_t)K, stream));
-            CK(cudaMemsetAsync(L.gstats, 0, sizeof(unsigned long long) * ST_COUNT * (size_t)K, stream));
-            CK(cudaEventRecord(gev[MAX_GROUPS], stream));
-            const long long G = n_graphs;
-            for (long long g = 0; g < K; g++) {
-                const long long v0 = n_views * g / K, v1 = n_views * (g + 1) / K, Vg = v1 - v0;
-                SchurParams Q = P;
-                const size_t o = (size_t)v0 * (size_t)n, og = (size_t)v0 * (size_t)G;
-                Q.V = (int)Vg;
-                Q.view_base = P.view_base + (uint32_t)v0;
-                Q.state += o; Q.lh += 2 * o; Q.rank += o; Q.blk += o; Q.candround += o;
-                Q.outoff += o;                                         // phase A's (round, key) snapshots live here
-                Q.pool += (size_t)v0 * (size_t)P.pool_cap;
-                Q.pool_cursor += v0;
-                Q.rem += og; Q.lvl += og; Q.cntI += og; Q.ovfseg += og; Q.thresh += og;
-                Q.minkey += 2 * og;                                    // [2][Vg * G] inside the [2 * V * G] array
-                Q.blockcnt += o / SEL_BLOCK + 2 * (size_t)g;
-                Q.wl += 2 * o + (size_t)g;
-                Q.dl += o + (size_t)g;
-                Q.low += 4 * o + 128 * (size_t)g;
-                Q.low_cap = (long long)(2 * (size_t)Vg * (size_t)n + 64);
-                Q.scratch = L.gscratch + (size_t)g * NSLOT * 3 * (size_t)L.scratch_cap;
-                Q.ctr = L.gctr + (size_t)g * CTR_COUNT;
-                Q.stats = L.gstats + (size_t)g * ST_COUNT;
-                const int bg = (int)((long long)blocks * (g + 1) / K - (long long)blocks * g / K);
-                CK(cudaStreamWaitEvent(gs[g], gev[MAX_GROUPS], 0));
-                CK(launch_eliminate(Q, gs[g], bg));
-                CK(cudaEventRecord(gev[g], gs[g]));
-                CK(cudaStreamWaitEvent(stream, gev[g], 0));
-            }
-            CK(launch_combine_groups((int)K, L.gctr, L.gstats, P.ctr, P.stats, stream));
+        std::vector<SchurParams>& groups = td->groups;
+        std::vector<int>& block_group = td->block_group;
+        groups.assign((size_t)K, P);
+        block_group.assign((size_t)blocks, 0);
+        CK(cudaMemsetAsync(L.gctr, 0, sizeof(int) * CTR_COUNT * (size_t)K, stream));
+        CK(cudaMemsetAsync(L.gstats, 0, sizeof(unsigned long long) * ST_COUNT * (size_t)K, stream));
+        const long long G = n_graphs;
+        long long slot0 = 0;
+        for (long long g = 0; g < K; g++) {
+            const long long v0 = n_views * g / K, v1 = n_views * (g + 1) / K, Vg = v1 - v0;
+            SchurParams& Q = groups[(size_t)g];
+            const size_t o = (size_t)v0 * (size_t)n, og = (size_t)v0 * (size_t)G;
+            Q.V = (int)Vg;
+            Q.view_base = P.view_base + (uint32_t)v0;
+            Q.state += o; Q.lh += 2 * o; Q.rank += o; Q.blk += o; Q.candround += o;
+            Q.outoff += o;                                         // phase A's (round, key) snapshots live here
+            Q.pool += (size_t)v0 * (size_t)P.pool_cap;
+            Q.pool_cursor += v0;
+            Q.rem += og; Q.lvl += og; Q.cntI += og; Q.ovfseg += og; Q.thresh += og;
+            Q.minkey += 2 * og;                                    // [2][Vg * G] inside the [2 * V * G] array
+            Q.blockcnt += o / SEL_BLOCK + 2 * (size_t)g;
+            Q.wl += 2 * o + (size_t)g;
+            Q.dl += o + (size_t)g;
+            Q.low += 4 * o + 128 * (size_t)g;
+            Q.low_cap = (long long)(2 * (size_t)Vg * (size_t)n + 64);
+            Q.ctr = L.gctr + (size_t)g * CTR_COUNT;
+            Q.stats = L.gstats + (size_t)g * ST_COUNT;
+            Q.gblock0 = (int)((long long)blocks * g / K);
+            Q.gblocks = (int)((long long)blocks * (g + 1) / K) - Q.gblock0;
+            Q.scratch = L.gscratch + (size_t)slot0 * 3 * (size_t)L.scratch_cap;
+            slot0 += Q.gblocks < NSLOT ? Q.gblocks : NSLOT;
+            for (int b = 0; b < Q.gblocks; b++) block_group[(size_t)(Q.gblock0 + b)] = (int)g;
         }
+        CK(cudaMemcpyAsync(L.gparams, groups.data(), sizeof(SchurParams) * (size_t)K, cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(L.block_group, block_group.data(), sizeof(int) * (size_t)blocks, cudaMemcpyHostToDevice, stream));
+        CK(launch_eliminate(L.gparams, L.block_group, blocks, o_v, o_n, flags, stream));
+        CK(launch_combine_groups((int)K, L.gctr, L.gstats, P.ctr, P.stats, stream));
     }
 #ifdef RLAP_DEBUG
     if (getenv("RLAP_DEBUG_SYNC")) {

@@ -3,14 +3,17 @@
 // 916-934: pop every remaining vertex, walk its list, sort, merge, push rows).
 //
 // No list walking here: the exact live count of every surviving vertex is known (the `live`
-// counters the elimination maintains), so the live entries are first regrouped owner-major by a
-// counting sort that streams the base CSR and the fill pool linearly:
+// counters the elimination maintains), so every survivor owns a staging segment of `live` slots:
 //   k_emit_prep     live counts of survivors            -> scan -> rawoff
-//   k_emit_scatter  base entries + pool entries, alive endpoints only -> raw[rawoff[owner] + cursor++]
-//   k_emit_sort_*   per survivor: sort its contiguous segment by neighbour, merge multi-edges in place
-//                   (<= 32 entries: warp shuffles in registers; <= 128: warp + smem; else thread block)
-//                                                       -> scan -> outoff
-//   k_emit_copy     compact copy into the caller's buffers (packed and/or [E',3] float64)
+//   k_emit_scatter  streams the fill pool: entries with two alive endpoints go to the TAIL of their owner's segment
+//   k_emit_fsort    per survivor with at most 32 fill entries: sorts them in place and looks for a multi-edge (two
+//                   fills to the same neighbour, or a fill parallel to a base edge). Without one - 99 % of the
+//                   survivors - the row count is the live count and nothing else is staged: "clean".
+//   the rest (a multi-edge, or more than 32 fills: the hubs) take the merge path: k_emit_base stages their alive
+//   base entries at the front of the segment, k_emit_sort_* sort the segment by neighbour and merge multi-edges
+//   with the fixed-point rule, in place                  -> scan -> outoff
+//   k_emit_write    clean survivors: the alive base entries (streamed from the CSR, ascending) and the sorted fills
+//                   are merged by rank straight into the caller's buffers; the others are copied from staging
 #include <stdlib.h>
 #include <mutex>
 #include "rlap_device.cuh"
@@ -38,9 +41,10 @@ __global__ void k_emit_prep(SchurParams P) {
     cursor_of(P)[idx] = 0;
 }
 
-// Base entries: an 8-lane tile per surviving vertex walks its (neighbour-ascending) CSR segment and writes the
-// entries whose neighbour is alive to the front of the vertex's staging segment, in order and without atomics;
-// rows longer than 64 are then served by the whole warp. cursor[v] = number of entries written.
+// Base entries of the survivors on the merge path (cursor == MERGE_PATH): an 8-lane tile per vertex walks its
+// (neighbour-ascending) CSR segment and writes the entries whose neighbour is alive to the front of the vertex's
+// staging segment, in order and without atomics; rows longer than 64 are then served by the whole warp.
+constexpr int MERGE_PATH = -1;
 __global__ void __launch_bounds__(256) k_emit_base(SchurParams P) {
     if (run_failed(P)) return;
     const long long VN = (long long)P.V * P.n;
@@ -54,7 +58,7 @@ __global__ void __launch_bounds__(256) k_emit_base(SchurParams P) {
         long long off = 0;
         size_t vb = 0;
         bool big = false;
-        if (idx < VN && P.state[idx] != 2) {
+        if (idx < VN && cursor_of(P)[idx] == MERGE_PATH) {
             const int v = (int)(idx % P.n);
             vb = (size_t)(idx - v);
             b = __ldg(P.ptr + v);
@@ -64,17 +68,14 @@ __global__ void __launch_bounds__(256) k_emit_base(SchurParams P) {
         }
         int cnt = 0;
         const int nbmax = __reduce_max_sync(RLAP_FULL_MASK, big ? 0 : nb);   // the tiles of a warp loop in lock step
-        {
-            for (int p0 = 0; p0 < nbmax; p0 += 8) {
-                const int p = p0 + tl;
-                int u = 0;
-                bool ok = !big && p < nb;
-                if (ok) { u = __ldg(P.col + b + p); ok = P.state[vb + u] != 2; }
-                const unsigned m = (__ballot_sync(RLAP_FULL_MASK, ok) >> (tile * 8)) & 0xffu;
-                if (ok) P.raw[off + cnt + __popc(m & tlt)] = pack_a((uint32_t)u, __ldg(P.w + b + p));
-                cnt += __popc(m);
-            }
-            if (!big && tl == 0 && nb > 0) cursor_of(P)[idx] = cnt;
+        for (int p0 = 0; p0 < nbmax; p0 += 8) {
+            const int p = p0 + tl;
+            int u = 0;
+            bool ok = !big && p < nb;
+            if (ok) { u = __ldg(P.col + b + p); ok = P.state[vb + u] != 2; }
+            const unsigned m = (__ballot_sync(RLAP_FULL_MASK, ok) >> (tile * 8)) & 0xffu;
+            if (ok) P.raw[off + cnt + __popc(m & tlt)] = pack_a((uint32_t)u, __ldg(P.w + b + p));
+            cnt += __popc(m);
         }
         __syncwarp();
         unsigned todo = __ballot_sync(RLAP_FULL_MASK, big && tl == 0);
@@ -94,14 +95,14 @@ __global__ void __launch_bounds__(256) k_emit_base(SchurParams P) {
                 if (ok) P.raw[koff + c + __popc(m & ((1u << lane) - 1u))] = pack_a((uint32_t)u, __ldg(P.w + kb + p));
                 c += __popc(m);
             }
-            if (lane == 0) cursor_of(P)[base + (k >> 3)] = c;
         }
     }
 }
 
 // Fill entries: grid-stride over the view's pool (blockIdx.y = view), one thread per fill edge = the two entries
 // (j <- k), (k <- j) it left in adjacent slots (reservations are even, so pairs never straddle); if both endpoints
-// are alive each entry goes behind the base entries of its owner
+// are alive each entry goes to the tail of its owner's staging segment, filled from the end backwards (the front is
+// where the alive base entries of a merge-path vertex go; cursor[v] counts the fills of v)
 __global__ void __launch_bounds__(256) k_emit_scatter(SchurParams P) {
     if (run_failed(P)) return;
     const int view = blockIdx.y;
@@ -115,26 +116,14 @@ __global__ void __launch_bounds__(256) k_emit_scatter(SchurParams P) {
         if (e0.w < 0) continue;                  // tombstones come in pairs as well
         const int j = e0.w, k = e0.x;
         if (P.state[vb + j] == 2 || P.state[vb + k] == 2) continue;
-        const long long p0 = P.rawoff[vb + j] + atomicAdd(cursor_of(P) + vb + j, 1);
-        const long long p1 = P.rawoff[vb + k] + atomicAdd(cursor_of(P) + vb + k, 1);
-        if (p0 < P.raw_cap && p1 < P.raw_cap) {
+        const long long p0 = P.rawoff[vb + j + 1] - 1 - atomicAdd(cursor_of(P) + vb + j, 1);
+        const long long p1 = P.rawoff[vb + k + 1] - 1 - atomicAdd(cursor_of(P) + vb + k, 1);
+        if (p0 >= 0 && p1 >= 0 && p0 < P.raw_cap && p1 < P.raw_cap) {
             P.raw[p0] = ((uint64_t)(uint32_t)k << 32) | (uint64_t)(uint32_t)e0.y;
             P.raw[p1] = ((uint64_t)(uint32_t)j << 32) | (uint64_t)(uint32_t)e0.y;
         } else {
             set_status(P, 6);
         }
-    }
-}
-
-// RLAP_FLAG_CHECK_LIVE: every survivor's scattered entry count must equal its live counter (self-check, stats[15])
-__global__ void k_emit_check(SchurParams P) {
-    const long long VN = (long long)P.V * P.n;
-    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= VN) return;
-    int c = cursor_of(P)[idx], rc = rawcnt_of(P)[idx];
-    if (c != rc) {
-        atomicAdd(P.stats + 7, 1ull);
-        atomicMax(P.stats + 6, ((unsigned long long)(unsigned)idx << 32) | ((unsigned long long)(unsigned)(c & 0xffff) << 16) | (unsigned)(rc & 0xffff));
     }
 }
 
@@ -295,86 +284,127 @@ __device__ void emit_sort_regs(const SchurParams& P, size_t idx, int lv, long lo
 // Segments of more than 32 entries are listed by size class in dense lists (the low-list buffers of the elimination
 // are free by now): a hub-heavy stretch of vertex ids (the old vertices of a preferential-attachment graph) would
 // otherwise hand all its big segments to the few warps that own that stretch.
-constexpr int N_CLASS = 6;      // 0..3: 64 / 128 / 256 / 512 entries (register sort), 4: <= CAP_CTA, 5: above
+constexpr int CAP_REGS = 512;   // largest segment sorted in registers
+constexpr int N_CLASS = 7;      // 0..3: 64 / 128 / 256 / 512 entries (register sort), 4: <= CAP_CTA, 5: above, 6: <= 32
 __device__ __forceinline__ unsigned int* class_list(const SchurParams& P, int c) {
     const size_t VN = (size_t)P.V * (size_t)P.n;
     if (c == 0) return P.wl;
     if (c == 1) return P.wl + VN;
     if (c == 5) return P.dl;
+    if (c == 6) return P.low + (size_t)3 * (VN + 16);
     return P.low + (size_t)(c - 2) * (VN + 16);
+}
+__device__ __forceinline__ int size_class(int lv) {
+    return lv <= 32 ? 6 : lv <= 64 ? 0 : lv <= 128 ? 1 : lv <= 256 ? 2 : lv <= CAP_REGS ? 3 : lv <= CAP_CTA ? 4 : 5;
 }
 __device__ __forceinline__ int* class_tail(const SchurParams& P, int c) { return P.ctr + CTR_EMIT_C0 + c; }
 
-constexpr int CAP_REGS = 512;   // largest segment sorted in registers
 constexpr int CAP_BIG = 12288;   // largest segment sorted in the shared memory of one SM (k_emit_sort_big)
 
-__global__ void __launch_bounds__(BLOCK_THREADS, 2) k_emit_sort_warp(SchurParams P) {
+constexpr int FSORT_MAX = 32;    // fills of a clean survivor
+constexpr int FS_LANE = 16;      // fills a single lane sorts in its shared-memory slot
+constexpr int FS_NB_MAX = 40;    // longest base row a single lane walks
+
+// Every survivor: sort its fill entries (the tail of its staging segment) by neighbour and look for a multi-edge.
+// A warp owns 32 consecutive vertices and reads their counts in one go. A vertex with at most FS_LANE fills is
+// handled by its lane alone (32 independent chains of loads per warp): insertion sort in a shared-memory slot, then a
+// merge walk over the neighbour ids of its base row for a fill parallel to a base edge. 17..32 fills: the warp sorts
+// them in registers, one vertex after the other. No multi-edge: the sorted fills go back in place and the survivor is
+// "clean" (its row count is its live count; cursor keeps the fill count). Otherwise, or with more than 32 fills, the
+// survivor takes the merge path (cursor = MERGE_PATH) and is listed by size class for the sort kernels.
+__global__ void __launch_bounds__(256) k_emit_fsort(SchurParams P) {
+    __shared__ uint64_t s_slot[8][FS_LANE * 32];
     const long long VN = (long long)P.V * P.n;
     const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
+    const bool failed = run_failed(P);
+    uint64_t* sl = s_slot[threadIdx.x >> 5] + lane;    // element e of this lane: sl[e * 32]
     for (long long base = gw * 32; base < VN; base += nw * 32) {
         const long long idx = base + lane;
-        int lv = 0;
-        long long off = 0;
-        if (idx < VN) {
+        int lv = 0, f = 0, b = 0, nb = 0;
+        long long end = 0;
+        if (idx < VN && !failed) {
             lv = rawcnt_of(P)[idx];
-            off = P.rawoff[idx];
-            if (lv == 0) P.outcnt[idx] = 0;
-        }
-        // segments of at most 16 entries: two at a time, one per half warp (16-lane tiles, all shuffles tile-wide)
-        {
-            typedef Tile<16> T;
-            const int tile = lane >> 4, tl = lane & 15;
-            const unsigned tlt = (1u << tl) - 1u;
-            unsigned tiny = __ballot_sync(RLAP_FULL_MASK, lv > 0 && lv <= 16);
-            while (tiny) {
-                const int k0 = __ffs(tiny) - 1;
-                tiny &= tiny - 1;
-                const int k1 = tiny ? __ffs(tiny) - 1 : -1;
-                tiny &= tiny - 1;                       // 0 & anything stays 0
-                const int k = tile == 0 ? k0 : k1;
-                const int klv = __shfl_sync(RLAP_FULL_MASK, lv, k & 31);
-                const long long koff = __shfl_sync(RLAP_FULL_MASK, off, k & 31);
-                uint64_t a = (k >= 0 && tl < klv) ? P.raw[koff + tl] : RLAP_PAD_A;
-                a = T::sort_u64(a);
-                unsigned long long q;
-                int shift, mult;
-                const unsigned hmask = T::merge_sorted(a, q, shift, false, mult);
-                if (k >= 0 && ((hmask >> tl) & 1u)) P.raw[koff + __popc(hmask & tlt)] = a;
-                if (k >= 0 && tl == 0) P.outcnt[base + k] = __popc(hmask);
+            if (lv > 0) {
+                f = cursor_of(P)[idx];
+                end = P.rawoff[idx + 1];
+                const int v = (int)(idx % P.n);
+                b = __ldg(P.ptr + v);
+                nb = __ldg(P.ptr + v + 1) - b;
             }
         }
-        // 17..32 entries: one vertex at a time, all 32 lanes on its (contiguous) segment
-        unsigned small = __ballot_sync(RLAP_FULL_MASK, lv > 16 && lv <= 32);
-        uint64_t a_next = RLAP_PAD_A;
-        if (small) {
-            int k = __ffs(small) - 1;
-            int klv = __shfl_sync(RLAP_FULL_MASK, lv, k);
-            long long koff = __shfl_sync(RLAP_FULL_MASK, off, k);
-            a_next = lane < klv ? P.raw[koff + lane] : RLAP_PAD_A;
-        }
-        while (small) {
-            const int k = __ffs(small) - 1;
-            small &= small - 1;
-            const long long koff = __shfl_sync(RLAP_FULL_MASK, off, k);
-            uint64_t a = a_next;
-            if (small) {  // prefetch the next vertex's segment while this one is sorted
-                int k2 = __ffs(small) - 1;
-                int klv2 = __shfl_sync(RLAP_FULL_MASK, lv, k2);
-                long long koff2 = __shfl_sync(RLAP_FULL_MASK, off, k2);
-                a_next = lane < klv2 ? P.raw[koff2 + lane] : RLAP_PAD_A;
+        if (idx < VN && (lv == 0 || f == 0)) P.outcnt[idx] = lv;      // eliminated / isolated, or no fills at all: clean
+        int cls = (lv > 0 && f > FSORT_MAX) ? size_class(lv) : -1;
+        const bool lanepath = lv > 0 && f > 0 && f <= FS_LANE && nb <= FS_NB_MAX;
+        if (lanepath) {
+            uint64_t* fp = P.raw + (end - f);
+#pragma unroll 4
+            for (int i = 0; i < f; i++) sl[i * 32] = fp[i];
+            bool dup = false;
+            for (int i = 1; i < f; i++) {
+                const uint64_t x = sl[i * 32];
+                int j = i - 1;
+                while (j >= 0) {
+                    const uint64_t y = sl[j * 32];
+                    if (a_nbr(y) <= a_nbr(x)) { dup |= a_nbr(y) == a_nbr(x); break; }
+                    sl[(j + 1) * 32] = y;
+                    j--;
+                }
+                sl[(j + 1) * 32] = x;
             }
+            if (!dup) {   // a fill parallel to a base edge of the vertex: both lists ascend, one merge walk
+                int i = 0;
+                uint32_t fn = a_nbr(sl[0]);
+                for (int p0 = 0; p0 < nb && i < f; p0 += 8) {
+                    uint32_t c8[8];
+#pragma unroll
+                    for (int k = 0; k < 8; k++) c8[k] = (p0 + k < nb) ? (uint32_t)__ldg(P.col + b + p0 + k) : 0xffffffffu;
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        while (i < f && fn < c8[k]) { i++; fn = i < f ? a_nbr(sl[i * 32]) : 0xffffffffu; }
+                        if (i < f && fn == c8[k]) dup = true;
+                    }
+                }
+            }
+            if (!dup) {
+                for (int i = 0; i < f; i++) fp[i] = sl[i * 32];
+                P.outcnt[idx] = lv;
+            } else {
+                cls = size_class(lv);
+            }
+        }
+        unsigned cand = __ballot_sync(RLAP_FULL_MASK, lv > 0 && f > 0 && f <= FSORT_MAX && !lanepath);
+        while (cand) {
+            const int k = __ffs(cand) - 1;
+            cand &= cand - 1;
+            const int kf = __shfl_sync(RLAP_FULL_MASK, f, k), kb = __shfl_sync(RLAP_FULL_MASK, b, k);
+            const int knb = __shfl_sync(RLAP_FULL_MASK, nb, k);
+            const long long kend = __shfl_sync(RLAP_FULL_MASK, end, k);
+            uint64_t a = lane < kf ? P.raw[kend - kf + lane] : RLAP_PAD_A;
             a = warp_sort_u64(a);
-            unsigned long long q;
-            int shift;
-            unsigned hmask = warp_merge_sorted(a, q, shift, false);
-            if ((hmask >> lane) & 1u) P.raw[koff + __popc(hmask & lt)] = a;
-            if (lane == 0) P.outcnt[base + k] = __popc(hmask);
+            const bool valid = a != RLAP_PAD_A;
+            const uint32_t nbr = a_nbr(a);
+            const uint32_t prev = __shfl_up_sync(RLAP_FULL_MASK, nbr, 1);
+            bool dup = valid && lane > 0 && prev == nbr;               // two fills to the same neighbour
+            if (valid) {                                               // a fill parallel to a base edge of the vertex
+                int lo = 0, hi = knb;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if ((uint32_t)__ldg(P.col + kb + mid) < nbr) lo = mid + 1; else hi = mid;
+                }
+                dup |= lo < knb && (uint32_t)__ldg(P.col + kb + lo) == nbr;
+            }
+            if (!__any_sync(RLAP_FULL_MASK, dup)) {
+                if (valid) P.raw[kend - kf + lane] = a;
+                if (lane == k) P.outcnt[idx] = lv;
+            } else if (lane == k) {
+                cls = size_class(lv);
+            }
         }
-        // bigger segments: dense per-class lists, one tail bump per class and warp pass
-        const int cls = lv <= 32 ? -1 : lv <= 64 ? 0 : lv <= 128 ? 1 : lv <= 256 ? 2 : lv <= CAP_REGS ? 3 : lv <= CAP_CTA ? 4 : 5;
+        // merge path: dense per-class lists, one tail bump per class and warp pass
+        if (cls >= 0) cursor_of(P)[idx] = MERGE_PATH;
         if (__any_sync(RLAP_FULL_MASK, cls >= 0)) {
 #pragma unroll
             for (int c = 0; c < N_CLASS; c++) {
@@ -386,6 +416,28 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_emit_sort_warp(SchurParams
                 if (cls == c) class_list(P, c)[pos0 + __popc(m & lt)] = (unsigned int)idx;
             }
         }
+    }
+}
+
+// merge path, segments of at most 32 entries: one warp each, one entry per lane
+__global__ void __launch_bounds__(256) k_emit_sort_small(SchurParams P) {
+    const int gw = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int nw = (int)(((long long)gridDim.x * blockDim.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const int end = *class_tail(P, 6);
+    const unsigned int* list = class_list(P, 6);
+    for (int it = gw; it < end; it += nw) {
+        const unsigned int idx = list[it];
+        const int lv = rawcnt_of(P)[idx];
+        const long long off = P.rawoff[idx];
+        uint64_t a = lane < lv ? P.raw[off + lane] : RLAP_PAD_A;
+        a = warp_sort_u64(a);
+        unsigned long long q;
+        int shift;
+        const unsigned hmask = warp_merge_sorted(a, q, shift, false);
+        if ((hmask >> lane) & 1u) P.raw[off + __popc(hmask & lt)] = a;
+        if (lane == 0) P.outcnt[idx] = __popc(hmask);
     }
 }
 
@@ -445,70 +497,194 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 1) k_emit_sort_big(SchurParams 
     }
 }
 
-// compact copy: merged segment of every survivor -> final rows. A warp owns 32 consecutive vertices; their rows are
-// contiguous in the output (outoff is the exclusive prefix of outcnt), so the warp walks that output range with all
-// lanes busy and finds the source vertex of every row by a 5-step search over the 32 start offsets.
-__global__ void __launch_bounds__(256) k_emit_copy(SchurParams P, int* out_row, int* out_col, float* out_w,
-                                                  double* out_f64) {
+// Final rows. A warp owns 32 consecutive vertices; their rows are contiguous in the output.
+//  * clean survivor (no multi-edge) of at most WR_LMAX rows: its LANE merges the alive base entries, streamed from
+//    the CSR in neighbour order, with its sorted fills into the warp's shared-memory staging area (32 independent
+//    chains of loads per warp); the warp then writes the staged rows out together, coalesced.
+//  * longer clean survivors: the warp merges by rank (an alive base entry goes to (alive base entries before it) +
+//    (fills with a smaller neighbour), fill i to i + (alive base entries with a smaller neighbour), both from
+//    shuffle binary searches).
+//  * merge-path survivors: copy of the merged staging segment.
+constexpr int WR_LMAX = 64;      // longest row a single lane merges
+constexpr int WR_NBMAX = 40;     // longest base row a single lane walks
+constexpr int WR_CAP = 1024;     // staged rows per pass (a pass may run over by one vertex: + WR_LMAX)
+constexpr int WR_WARPS = 4;
+__global__ void __launch_bounds__(WR_WARPS * 32) k_emit_write(SchurParams P, int* out_row, int* out_col, float* out_w,
+                                                              double* out_f64) {
+    __shared__ uint64_t s_stage[WR_WARPS][WR_CAP + WR_LMAX];
+    if (run_failed(P)) return;
     const long long VN = (long long)P.V * P.n;
     const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
     const int lane = threadIdx.x & 31;
-    // the counts and offsets of the next 32 vertices are requested before the rows of the current ones are copied
-    long long nsrc = 0, ndst = 0;
-    int nL = 0;
-    if (gw * 32 + lane < VN) {
-        nL = P.outcnt[gw * 32 + lane];
-        nsrc = P.rawoff[gw * 32 + lane];
-        ndst = P.outoff[gw * 32 + lane];
-    }
+    const unsigned lt = (1u << lane) - 1u;
+    const bool check = (P.flags & 8) != 0;
+    uint64_t* stage = s_stage[threadIdx.x >> 5];
+    auto put = [&](long long w, uint32_t r, int c, float wt) {
+        if (out_row) {
+            __stcs(out_row + w, (int)r);
+            if (out_col) __stcs(out_col + w, c);      // NULL: the caller rebuilds the columns from the column pointers
+            __stcs(out_w + w, wt);
+        }
+        if (out_f64) {
+            out_f64[w * 3 + 0] = (double)r;
+            out_f64[w * 3 + 1] = (double)c;
+            out_f64[w * 3 + 2] = (double)wt;
+        }
+    };
+    auto mismatch = [&](long long vidx, int got, int want) {   // RLAP_FLAG_CHECK_LIVE: alive base entries + fills must be the live count
+        atomicAdd(P.stats + 7, 1ull);
+        atomicMax(P.stats + 6, ((unsigned long long)(unsigned)vidx << 32) | ((unsigned long long)(unsigned)(got & 0xffff) << 16) | (unsigned)(want & 0xffff));
+    };
     for (long long base = gw * 32; base < VN; base += nw * 32) {
         const long long idx = base + lane;
-        const long long src = nsrc, dst = ndst;
-        const int L = nL;
-        {
-            const long long nidx = idx + nw * 32;
-            nL = 0; nsrc = 0; ndst = 0;
-            if (nidx < VN) {
-                nL = P.outcnt[nidx];
-                nsrc = P.rawoff[nidx];
-                ndst = P.outoff[nidx];
+        int L = 0, f = 0, b = 0, nb = 0, v = 0;
+        long long dst = 0, src = 0, end = 0;
+        if (idx < VN) {
+            L = P.outcnt[idx];
+            if (L > 0) {
+                f = cursor_of(P)[idx];
+                dst = P.outoff[idx];
+                src = P.rawoff[idx];
+                end = P.rawoff[idx + 1];
+                v = (int)(idx % P.n);
+                b = __ldg(P.ptr + v);
+                nb = __ldg(P.ptr + v + 1) - b;
             }
         }
-        const long long dst0 = __shfl_sync(RLAP_FULL_MASK, dst, 0);
-        // start of lane i's rows relative to the warp's output range; lanes past VN inherit the end of the range
-        int rel = (int)(dst - dst0);
-        const int total = __shfl_sync(RLAP_FULL_MASK, rel + L, 31 < (VN - base - 1) ? 31 : (int)(VN - base - 1));
-        if (idx >= VN) rel = total;
-        const int v0 = (int)(base % P.n);
-#pragma unroll 4
-        for (int o0 = 0; o0 < total; o0 += 32) {
-            const int o = o0 + lane;
-            // last lane i with rel_i <= o (rows of empty vertices are skipped: equal offsets resolve to the last one)
-            int lo = 0;
+        // ---- lane tier
+        const bool staged = L > 0 && f != MERGE_PATH && L <= WR_LMAX && nb <= WR_NBMAX;
+        const int Ls = staged ? L : 0;
+        int srel = Ls;   // exclusive prefix of the staged row counts
 #pragma unroll
-            for (int step = 16; step > 0; step >>= 1) {
-                const int r = __shfl_sync(RLAP_FULL_MASK, rel, (lo + step) & 31);
-                if (lo + step < 32 && r <= o) lo += step;
-            }
-            const long long ksrc = __shfl_sync(RLAP_FULL_MASK, src, lo);
-            const int krel = __shfl_sync(RLAP_FULL_MASK, rel, lo);
-            if (o < total) {
-                const uint64_t a = __ldcs((const unsigned long long*)P.raw + ksrc + (o - krel));   // read once
-                int v = v0 + lo;
-                while (v >= P.n) v -= P.n;   // the 32 vertices may straddle view boundaries (tiny graphs: several)
-                const long long w = dst0 + o;
-                if (out_row) {
-                    __stcs(out_row + w, (int)a_nbr(a));
-                    if (out_col) __stcs(out_col + w, v);      // NULL: the caller rebuilds the columns from the column pointers
-                    __stcs(out_w + w, a_w(a));
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(RLAP_FULL_MASK, srel, d);
+            if (lane >= d) srel += t;
+        }
+        const int stot = __shfl_sync(RLAP_FULL_MASK, srel, 31);
+        srel -= Ls;
+        int s0 = 0;
+        for (int pass = 0; pass * WR_CAP < stot; pass++) {
+            const bool mine = staged && srel / WR_CAP == pass;
+            if (mine) {
+                uint64_t* st = stage + (srel - pass * WR_CAP);
+                const size_t vb = (size_t)(idx - v);
+                const uint64_t* fp = P.raw + (end - f);   // sorted fills
+                // the fills are parked at the end of this lane's staging span and merged forward in place: the output
+                // position (base entries emitted + fills emitted) never passes the next unread fill
+                uint64_t* sf = st + (L - f);
+#pragma unroll 4
+                for (int i = 0; i < f; i++) sf[i] = fp[i];
+                int r = 0, i = 0;
+                uint32_t nfn = f > 0 ? a_nbr(sf[0]) : 0xffffffffu;   // no fill left: the largest id, never "smaller"
+                for (int p0 = 0; p0 < nb; p0 += 8) {
+                    uint32_t c8[8];
+                    float w8[8];
+                    uint8_t s8[8];
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        const bool in = p0 + k < nb;
+                        c8[k] = in ? (uint32_t)__ldg(P.col + b + p0 + k) : 0xffffffffu;
+                        w8[k] = in ? __ldg(P.w + b + p0 + k) : 0.f;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 8; k++) s8[k] = (c8[k] != 0xffffffffu) ? P.state[vb + c8[k]] : (uint8_t)2;
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        if (s8[k] != 2) {
+                            while (nfn < c8[k]) {
+                                if (r < L) st[r] = sf[i];
+                                r++; i++;
+                                nfn = i < f ? a_nbr(sf[i]) : 0xffffffffu;
+                            }
+                            if (r < L) st[r] = pack_a(c8[k], w8[k]);
+                            r++;
+                        }
+                    }
                 }
-                if (out_f64) {
-                    out_f64[w * 3 + 0] = (double)a_nbr(a);
-                    out_f64[w * 3 + 1] = (double)v;
-                    out_f64[w * 3 + 2] = (double)a_w(a);
+                r += f - i;   // the remaining fills are already in place
+                if (check && r != L) mismatch(idx, r, L);
+            }
+            __syncwarp();
+            // staged rows [s0, s1) of this pass -> output, coalesced; the owner of staged row s is the last lane whose
+            // prefix is <= s (lanes that stage nothing share the prefix of their successor)
+            const int s1 = __reduce_max_sync(RLAP_FULL_MASK, mine ? srel + Ls : s0);
+            for (int sb = s0; sb < s1; sb += 32) {
+                const int sidx = sb + lane;
+                int lo = 0;
+#pragma unroll
+                for (int step = 16; step > 0; step >>= 1) {
+                    const int r = __shfl_sync(RLAP_FULL_MASK, srel, (lo + step) & 31);
+                    if (lo + step < 32 && r <= sidx) lo += step;
+                }
+                const long long odst = __shfl_sync(RLAP_FULL_MASK, dst, lo);
+                const int osrel = __shfl_sync(RLAP_FULL_MASK, srel, lo);
+                const int ov = __shfl_sync(RLAP_FULL_MASK, v, lo);
+                if (sidx < s1) {
+                    const uint64_t a = stage[sidx - pass * WR_CAP];
+                    put(odst + (sidx - osrel), a_nbr(a), ov, a_w(a));
                 }
             }
+            s0 = s1;
+            __syncwarp();
+        }
+        // ---- cooperative tier: the survivors the lanes did not take
+        unsigned todo = __ballot_sync(RLAP_FULL_MASK, L > 0 && !staged);
+        while (todo) {
+            const int k = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int kL = __shfl_sync(RLAP_FULL_MASK, L, k), kf = __shfl_sync(RLAP_FULL_MASK, f, k);
+            const int kv = __shfl_sync(RLAP_FULL_MASK, v, k);
+            const long long kdst = __shfl_sync(RLAP_FULL_MASK, dst, k);
+            if (kf == MERGE_PATH) {
+                const long long ksrc = __shfl_sync(RLAP_FULL_MASK, src, k);
+                for (int o = lane; o < kL; o += 32) {
+                    const uint64_t a = __ldcs((const unsigned long long*)P.raw + ksrc + o);
+                    put(kdst + o, a_nbr(a), kv, a_w(a));
+                }
+                continue;
+            }
+            const int kb = __shfl_sync(RLAP_FULL_MASK, b, k), knb = __shfl_sync(RLAP_FULL_MASK, nb, k);
+            const long long kend = __shfl_sync(RLAP_FULL_MASK, end, k);
+            const size_t vb = (size_t)(base + k - kv);
+            // sorted fills, one per lane; a lane without one holds the largest id, so it never counts as "smaller"
+            const uint64_t fa = lane < kf ? __ldcs((const unsigned long long*)P.raw + kend - kf + lane) : RLAP_PAD_A;
+            const uint32_t fnbr = a_nbr(fa);
+            int cb = 0;     // alive base entries with a smaller neighbour than this lane's fill
+            int run = 0;    // alive base entries of the chunks done so far
+            for (int p0 = 0; p0 < knb; p0 += 32) {
+                const int p = p0 + lane;
+                uint32_t c = 0xffffffffu;
+                float w = 0.f;
+                bool alive = false;
+                if (p < knb) {
+                    c = (uint32_t)__ldg(P.col + kb + p);
+                    w = __ldg(P.w + kb + p);
+                    alive = P.state[vb + c] != 2;
+                }
+                const unsigned mask = __ballot_sync(RLAP_FULL_MASK, alive);
+                // fills with a smaller neighbour than this lane's base entry
+                int lo = 0, hi = kf;
+#pragma unroll
+                for (int it = 0; it < 6; it++) {
+                    const int mid = (lo + hi) >> 1;
+                    const uint32_t fm = __shfl_sync(RLAP_FULL_MASK, fnbr, mid & 31);
+                    if (lo < hi) { if (fm < c) lo = mid + 1; else hi = mid; }
+                }
+                if (alive) put(kdst + run + __popc(mask & lt) + lo, c, kv, w);
+                // base entries of this chunk with a smaller neighbour than this lane's fill (the chunk is ascending)
+                int lo2 = 0, hi2 = 32;
+#pragma unroll
+                for (int it = 0; it < 6; it++) {
+                    const int mid = (lo2 + hi2) >> 1;
+                    const uint32_t cm = __shfl_sync(RLAP_FULL_MASK, c, mid & 31);
+                    if (lo2 < hi2) { if (cm < fnbr) lo2 = mid + 1; else hi2 = mid; }
+                }
+                cb += __popc(mask & (lo2 >= 32 ? 0xffffffffu : ((1u << lo2) - 1u)));
+                run += __popc(mask);
+            }
+            if (lane < kf) put(kdst + lane + cb, fnbr, kv, a_w(fa));
+            if (check && lane == 0 && run + kf != kL) mismatch(base + k, run + kf, kL);
         }
     }
 }
@@ -548,21 +724,24 @@ cudaError_t launch_emit_count(const SchurParams& P, long long* total_dev, cudaSt
     e = launch_exclusive_scan<long long>(P.blk, VN, P.rawoff, P.blocksum, nullptr, stream);
     if (e != cudaSuccess) return e;
     {
-        long long bx = (VN / 4 * 32 + 255) / 256;   // one 8-lane tile per vertex
-        if (bx < 1) bx = 1;
-        if (bx > 148 * 16) bx = 148 * 16;
-        k_emit_base<<<(unsigned)bx, 256, 0, stream>>>(P);
         long long work = P.pool_cap / 2;
-        bx = (work + 256 * 4 - 1) / (256 * 4);
+        long long bx = (work + 256 * 4 - 1) / (256 * 4);
         if (bx < 1) bx = 1;
         if (bx > 148 * 8) bx = 148 * 8;
         k_emit_scatter<<<dim3((unsigned)bx, (unsigned)P.V), 256, 0, stream>>>(P);
+        bx = (VN + 255) / 256;            // one warp per 32 vertices
+        if (bx < 1) bx = 1;
+        if (bx > 148 * 16) bx = 148 * 16;
+        k_emit_fsort<<<(unsigned)bx, 256, 0, stream>>>(P);
+        bx = (VN / 4 * 32 + 255) / 256;   // one 8-lane tile per vertex
+        if (bx < 1) bx = 1;
+        if (bx > 148 * 16) bx = 148 * 16;
+        k_emit_base<<<(unsigned)bx, 256, 0, stream>>>(P);
     }
-    if (P.flags & 8) k_emit_check<<<(unsigned)((VN + 255) / 256), 256, 0, stream>>>(P);   // RLAP_FLAG_CHECK_LIVE
     int blocks = 0;
     e = eliminate_grid(&blocks);
     if (e != cudaSuccess) return e;
-    k_emit_sort_warp<<<blocks * 2, BLOCK_THREADS, 0, stream>>>(P);
+    k_emit_sort_small<<<148 * 8, 256, 0, stream>>>(P);
     k_emit_sort_mid<2><<<148 * 8, 256, 0, stream>>>(P);
     k_emit_sort_mid<4><<<148 * 8, 256, 0, stream>>>(P);
     k_emit_sort_mid<8><<<148 * 4, 256, 0, stream>>>(P);
@@ -581,10 +760,10 @@ cudaError_t launch_emit_colptr(const SchurParams& P, int* colptr, cudaStream_t s
 cudaError_t launch_emit_write(const SchurParams& P, int* out_row, int* out_col, float* out_w, double* out_f64,
                               cudaStream_t stream) {
     const long long VN = (long long)P.V * P.n;
-    long long bx = (VN + 255) / 256;  // one warp per 32 vertices
+    long long bx = (VN + 32 * WR_WARPS - 1) / (32 * WR_WARPS);  // one warp per 32 vertices
     if (bx < 1) bx = 1;
-    if (bx > 148 * 16) bx = 148 * 16;
-    k_emit_copy<<<(unsigned)bx, 256, 0, stream>>>(P, out_row, out_col, out_w, out_f64);
+    if (bx > 148 * 24) bx = 148 * 24;
+    k_emit_write<<<(unsigned)bx, WR_WARPS * 32, 0, stream>>>(P, out_row, out_col, out_w, out_f64);
     return cudaGetLastError();
 }
 

@@ -13,15 +13,12 @@
 //     binary-search sampling -> atomic append of the fill edges to both endpoints.
 // The sequential specification this file implements bit for bit is oracle/rlap_oracle.cc (keyed mode)
 // and DESIGN.md §3.
-#include <cooperative_groups.h>
 #include <stdio.h>
 #include <mutex>
 #include "rlap_device.cuh"
 #include "schur.cuh"
 #include "scan.cuh"
 #include "star.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace rlap {
 
@@ -835,7 +832,7 @@ __device__ __forceinline__ StarBuf warp_region_buf(const PT& P, uint64_t* smem) 
 template <class PT>
 __device__ void run_warp_items(const PT& P, const RoundCtx& rc, uint64_t* smem, CtaScratch* cs, int* next,
                                int start, int end, LocalStats* ls, LowAppender& la) {
-    const int nw = (int)((gridDim.x * blockDim.x) >> 5);
+    const int nw = (int)((P.gblocks * blockDim.x) >> 5);
     const int lane = threadIdx.x & 31;
     StarBuf sb = warp_region_buf(P, smem);
     uint64_t* fbuf = sb.A;   // 32 x FCAP staged fill entries of the register tiles; the shared-memory path reuses the area
@@ -990,19 +987,20 @@ __device__ void run_warp_items(const PT& P, const RoundCtx& rc, uint64_t* smem, 
 template <class PT>
 __device__ void run_block_items(const PT& P, const RoundCtx& rc, uint64_t* smem, CtaScratch* cs, int start,
                                 int end, LocalStats* ls, LowAppender& la) {
-    for (int it = start + (int)blockIdx.x; it < end; it += (int)gridDim.x) {
+    const int lb = (int)blockIdx.x - P.gblock0;   // block index inside the view group
+    for (int it = start + lb; it < end; it += P.gblocks) {
         unsigned int idx = __ldcg(P.dl + it);
         int view = (int)(idx / (unsigned)P.n), v = (int)(idx % (unsigned)P.n);
         if (ldcg_i32(live_p(P, idx)) <= CAP_CTA) eliminate_star<true>(P, rc, view, v, cta_buf(smem), cs, ls, la);
         __syncthreads();
     }
-    const int nslot = min(NSLOT, (int)gridDim.x);   // a view group may run on fewer blocks than there are slots
-    if ((int)blockIdx.x < nslot) {
+    const int nslot = min(NSLOT, P.gblocks);   // a view group may run on fewer blocks than there are slots
+    if (lb < nslot) {
         int j = 0;
         for (int it = start; it < end; it++) {
             unsigned int idx = __ldcg(P.dl + it);
             if (ldcg_i32(live_p(P, idx)) <= CAP_CTA) continue;
-            if ((j++ % nslot) != (int)blockIdx.x) continue;
+            if ((j++ % nslot) != lb) continue;
             int view = (int)(idx / (unsigned)P.n), v = (int)(idx % (unsigned)P.n);
             eliminate_star<true>(P, rc, view, v, scratch_buf(P), cs, ls, la);
             __syncthreads();
@@ -1010,16 +1008,43 @@ __device__ void run_block_items(const PT& P, const RoundCtx& rc, uint64_t* smem,
     }
 }
 
+// Barrier of one view group (the blocks [gblock0, gblock0 + gblocks) of a cooperative launch, all co-resident): a
+// counter of arrivals and a generation word in the group's control block. A group of one block needs no global
+// barrier at all: its phases are separated by __syncthreads alone.
+__device__ __forceinline__ void group_sync(int* bar, int nblocks) {
+    __syncthreads();
+    if (nblocks > 1) {
+        if (threadIdx.x == 0) {
+            volatile int* gen_p = bar + 1;
+            const int gen = *gen_p;
+            __threadfence();
+            if (atomicAdd(bar, 1) == nblocks - 1) {
+                *(volatile int*)bar = 0;
+                __threadfence();
+                atomicAdd(bar + 1, 1);
+            } else {
+                while (*gen_p == gen) {}
+            }
+            __threadfence();
+        }
+        __syncthreads();
+    }
+}
+
+// One cooperative launch serves every view group of a call: block b works on the parameter block garr[block_group[b]].
 template <int OV, int ON, bool FULL>
-__global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(const __grid_constant__ ModeParams<OV, ON, FULL> P) {
+__global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(const ModeParams<OV, ON, FULL>* __restrict__ garr,
+                                                                const int* __restrict__ block_group) {
+    const ModeParams<OV, ON, FULL>& P = garr[__ldg(block_group + blockIdx.x)];
     extern __shared__ __align__(16) uint64_t smem[];
     __shared__ CtaScratch cs;
     __shared__ int s_next, s_nsel;
     __shared__ unsigned int s_lowbuf[WARPS_PER_BLOCK][LOWBUF];
     __shared__ LocalStats s_stats[WARPS_PER_BLOCK];
-    cg::grid_group grid = cg::this_grid();
-    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long nthr = (long long)gridDim.x * blockDim.x;
+    const long long tid = (long long)((int)blockIdx.x - P.gblock0) * blockDim.x + threadIdx.x;   // inside the view group
+    const long long nthr = (long long)P.gblocks * blockDim.x;
+    int* const bar = P.ctr + CTR_BAR;
+    const int gblocks = P.gblocks;
     const long long VN = (long long)P.V * P.n;
     const long long VG = (long long)P.V * P.G;
     const bool random_order = (P.o_v == 0);
@@ -1057,7 +1082,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(const __grid_con
         }
     }
     for (long long s = tid; s < P.V; s += nthr) P.pool_cursor[s] = 0ull;
-    grid.sync();
+    group_sync(bar, gblocks);
 
     // phase timing (block 0, thread 0; nanoseconds between grid barriers, waits included)
     unsigned long long tmark = 0;
@@ -1085,7 +1110,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(const __grid_con
         unsigned long long t0 = 0;
         if (wait_timers && (threadIdx.x & 31) == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
 #endif
-        grid.sync();
+        group_sync(bar, gblocks);
 #ifdef RLAP_DEBUG
         if (wait_timers && (threadIdx.x & 31) == 0) {
             unsigned long long t1;
@@ -1600,7 +1625,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(const __grid_con
                     }
                     if (lane == 0) P.blockcnt[bk] = c;
                 }
-                grid.sync();
+                group_sync(bar, gblocks);
                 for (long long s = gw; s < VG; s += nw) {
                     int need = ldcg_i32(P.rem + s);
                     if (ldcg_i32(P.cntI + s) <= need) continue;
@@ -1795,14 +1820,10 @@ cudaError_t eliminate_grid(int* blocks_out) {
     return cudaSuccess;
 }
 
-cudaError_t launch_eliminate(const SchurParams& P, cudaStream_t stream, int blocks_req) {
-    int blocks = 0;
-    cudaError_t e = eliminate_grid(&blocks);
-    if (e != cudaSuccess) return e;
-    if (blocks_req > 0 && blocks_req < blocks) blocks = blocks_req;
-    SchurParams Pc = P;
-    void* args[] = {(void*)&Pc};
-    const int m = mode_index(P.o_v, P.o_n, (P.flags & 1) != 0);
+cudaError_t launch_eliminate(const SchurParams* groups_dev, const int* block_group_dev, int blocks, int o_v, int o_n,
+                             int flags, cudaStream_t stream) {
+    void* args[] = {(void*)&groups_dev, (void*)&block_group_dev};
+    const int m = mode_index(o_v, o_n, (flags & 1) != 0);
     return cudaLaunchCooperativeKernel(mode_kernel(m), dim3(blocks), dim3(BLOCK_THREADS), args,
                                        eliminate_smem_bytes(mode_needs_keys(m)), stream);
 }

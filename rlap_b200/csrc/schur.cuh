@@ -35,6 +35,7 @@ enum {
     CTR_LOWOVF0 = 16,    // degree mode: the low list of that parity overflowed (every segment rescans)
     CTR_LOWOVF1 = 17,
     CTR_STEAL0 = 18,     // elimination phase: cursor of the part of the work list any warp may fetch (18..20, by round % 3)
+    CTR_BAR = 21,        // barrier of the view group: arrivals (21) and generation (22)
     CTR_COUNT = 24
 };
 
@@ -101,6 +102,8 @@ struct SchurParams {
     long long low_cap;
     int* ctr;          // [CTR_COUNT]
     unsigned long long* stats;  // [ST_COUNT]
+    // the blocks [gblock0, gblock0 + gblocks) of the launch work on this parameter block (a view group)
+    int gblock0, gblocks;
     // global scratch for stars larger than CAP_CTA: slot b = 3 * scratch_cap u64 for block b
     uint64_t* scratch;
     int scratch_cap;

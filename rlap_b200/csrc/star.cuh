@@ -28,7 +28,7 @@ __device__ __forceinline__ StarBuf cta_buf(uint64_t* smem) {
 }
 __device__ __forceinline__ StarBuf scratch_buf(const SchurParams& P) {
     StarBuf sb;
-    sb.A = P.scratch + (size_t)blockIdx.x * 3 * (size_t)P.scratch_cap;
+    sb.A = P.scratch + (size_t)((int)blockIdx.x - P.gblock0) * 3 * (size_t)P.scratch_cap;
     sb.Q = sb.A + P.scratch_cap;
     sb.K = sb.Q + P.scratch_cap;
     sb.cap = P.scratch_cap;
