@@ -1,16 +1,24 @@
 #!/usr/bin/env python
-"""bench.py — rLap views/s on the ogbn-arxiv-shaped graph (BASELINE.json configs[3]).
+"""bench.py — rLap views/s on the shapes BASELINE.json names (default: the ogbn-arxiv-shaped headline, configs[3]).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--views V] [--impl ours|reference]
+  python bench.py [--config C1|C2|C3|C4|C5] [--o_v ..] [--o_n ..] [--gpus N] [--steps K] [--warmup W] [--views V]
+                  [--impl ours|reference]
 
-One "step" = one pass of the hot path over one batch: ingest (COO -> CSR, validation) of the
-arxiv-shaped Barabasi-Albert graph (169,343 nodes, ~2.37M directed edges, synthetic, seeded) plus
-V independent degree/asc views with num_remove = 50 % (ordering, elimination, emission), on every GPU.
-Views are sharded over GPUs by view id (weak scaling: V views per GPU per step, no data-path
-collective). `value` is whole-job views/s with the edge list resident in HBM; `e2e` is the same
-through the public API with HOST buffers (pinned edge_index in, packed rows out, copies inside the
-timed region). `--impl reference` times the reference's own CPU implementation (oracle/_ref, the
+One "step" = one pass of the hot path over one batch: ingest (COO -> CSR, validation) of the config's synthetic
+graph plus V independent views (ordering, elimination, emission) on every GPU. Views are sharded over GPUs by view id
+(weak scaling: V views per GPU per step, no data-path collective). `value` is whole-job views/s with the edge list
+resident in HBM; `e2e` is the same through the public API with HOST buffers (pinned edge_index in, packed rows out,
+copies inside the timed region). `--impl reference` times the reference's own CPU implementation (oracle/_ref, the
 unmodified C++ built against a container-only Eigen stand-in) on all host cores.
+
+Configs (BASELINE.json `configs`):
+  C1  BA n=100, m=50, num_remove=50, random/asc (the reference's README / test example), 256 views per step
+  C2  Cora-shaped SBM n=2708, 10556 directed edges, num_remove=812 (30 %), any o_v/o_n (default degree/asc), 256 views
+  C3  PROTEINS-shaped batch of 1113 graphs (~39 nodes each), 2 views of every graph per step, num_remove = n_g // 2 per
+      graph; a "view" is one augmented graph (2226 per step). The reference arm follows the reference's own call
+      pattern: unions of 128 graphs per call (scripts/graph_shared.py:139-146, DataLoader(batch_size=128))
+  C4  arxiv-shaped BA n=169343, m=7 (~2.37 M directed edges), num_remove=50 %, degree/asc, 64 views per step (headline)
+  C5  products-shaped SBM n=2449029, 123.7 M directed edges, coarsen, num_remove=50 %, 4 views per step
 """
 import argparse
 import json
@@ -26,29 +34,76 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-N_NODES = 169343
-BA_M = 7
-O_V, O_N = "degree", "asc"
 METRIC = "rlap_views_per_sec"
 UNIT = "views/s"
 
+CONFIGS = {
+    "C1": dict(o_v="random", o_n="asc", views=256,
+               workload="C1 Barabasi-Albert graph n=100 m=50 (README/tests example), num_remove=50"),
+    "C2": dict(o_v="degree", o_n="asc", views=256,
+               workload="C2 Cora-shaped SBM n=2708 E=10556 directed, num_remove=812 (30%)"),
+    "C3": dict(o_v="random", o_n="asc", views=2,
+               workload="C3 PROTEINS-shaped batch of 1113 graphs (~39 nodes each), num_remove=50% per graph, one view = one augmented graph"),
+    "C4": dict(o_v="degree", o_n="asc", views=64,
+               workload="C4 arxiv-shaped BA graph n=169343 E~2.37M directed, num_remove=50%"),
+    "C5": dict(o_v="coarsen", o_n="asc", views=4,
+               workload="C5 products-shaped SBM n=2449029 E~123.7M directed, num_remove=50%"),
+}
 
-def make_graph():
-    """arxiv-shaped BA graph, cached under /tmp (generation is a python loop of a few seconds)"""
-    path = f"/tmp/rlap_b200_ba_{N_NODES}_{BA_M}_seed0.npy"
+
+class Workload:
+    """the synthetic input of one config: edge_index (numpy on the host, or a torch tensor for C5), node count, graph
+    pointer of a batch, removals, and how many "views" one view of the whole input counts for"""
+
+    def __init__(self, name, device=None):
+        from rlap_b200 import graphs
+        self.name = name
+        self.graph_ptr = None
+        self.units = 1
+        self.ei_torch = None
+        if name == "C1":
+            self.n, self.ei = 100, graphs.barabasi_albert(100, 50, seed=0)
+            self.num_remove = 50
+        elif name == "C2":
+            self.n, self.ei = 2708, graphs.sbm(2708, 7, 5278, seed=0)
+            self.num_remove = 812
+        elif name == "C3":
+            self.ei, ptr = graphs.proteins_like_batch(1113, seed=0)
+            self.n, self.graph_ptr = int(ptr[-1]), ptr
+            self.num_remove = np.diff(ptr) // 2
+            self.units = 1113
+        elif name == "C4":
+            self.n = 169343
+            self.ei = _cached(f"/tmp/rlap_b200_ba_{self.n}_7_seed0.npy", lambda: graphs.barabasi_albert(self.n, 7, seed=0))
+            self.num_remove = self.n // 2
+        elif name == "C5":
+            import torch
+            self.n = 2449029
+            dev = device if device is not None else "cpu"
+            self.ei_torch = graphs.sbm_torch(self.n, 47, 61859140, seed=0, device=dev)
+            self.ei = None
+            self.num_remove = self.n // 2
+        else:
+            raise ValueError(name)
+        self.E = int(self.ei.shape[1]) if self.ei is not None else int(self.ei_torch.shape[1])
+
+    def edge_index_numpy(self):
+        return self.ei if self.ei is not None else self.ei_torch.cpu().numpy()
+
+
+def _cached(path, make):
     if os.path.exists(path):
         try:
             return np.load(path)
         except Exception:
             pass
-    from rlap_b200 import graphs
-    ei = graphs.barabasi_albert(N_NODES, BA_M, seed=0)
+    arr = make()
     try:
-        np.save(path + f".{os.getpid()}.tmp.npy", ei)
+        np.save(path + f".{os.getpid()}.tmp.npy", arr)
         os.replace(path + f".{os.getpid()}.tmp.npy", path)
     except Exception:
         pass
-    return ei
+    return arr
 
 
 def peaks():
@@ -102,32 +157,52 @@ class ClockSampler(threading.Thread):
 # ----------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the unmodified reference C++ on the host cores
 # ----------------------------------------------------------------------------------------------
+def _ref_calls(wl):
+    """the reference's call pattern for one view of the whole input: [(edge_info, n, t)] (C3: unions of 128 graphs)"""
+    ei = wl.edge_index_numpy()
+    if wl.graph_ptr is None:
+        info = np.concatenate([ei.T.astype(np.float64), np.ones((ei.shape[1], 1))], axis=1)
+        return [(info, wl.n, int(wl.num_remove))]
+    calls = []
+    ptr = wl.graph_ptr
+    G = len(ptr) - 1
+    owner = np.searchsorted(ptr, ei[1], side="right") - 1
+    for g0 in range(0, G, 128):
+        g1 = min(g0 + 128, G)
+        lo, hi = int(ptr[g0]), int(ptr[g1])
+        sel = (owner >= g0) & (owner < g1)
+        sub = ei[:, sel] - lo
+        info = np.concatenate([sub.T.astype(np.float64), np.ones((sub.shape[1], 1))], axis=1)
+        calls.append((info, hi - lo, int(0.5 * (hi - lo))))      # num_remove = int(frac * num_nodes) of the union
+    return calls
+
+
 def _ref_worker(args):
-    info_path, n, t, views = args
+    path, o_v, o_n, views = args
     from oracle import ref
-    info = np.load(info_path, mmap_mode="r")
-    info = np.ascontiguousarray(info)
+    data = np.load(path, allow_pickle=True)
+    calls = [(np.ascontiguousarray(c[0]), int(c[1]), int(c[2])) for c in data]
     t0 = time.perf_counter()
     rows = 0
     for _ in range(views):
-        rows += ref.approximate_cholesky(info, n, t, O_V, O_N).shape[0]
+        for info, n, t in calls:
+            rows += ref.approximate_cholesky(info, n, t, o_v, o_n).shape[0]
     return time.perf_counter() - t0, rows
 
 
-def cpu_reference_throughput(ei, procs, views_per_proc=1):
-    """one process per core, each producing `views_per_proc` views with the reference build;
-    returns (views/s, wall seconds, kind)"""
+def cpu_reference_throughput(calls, o_v, o_n, procs, views_per_proc=1):
+    """one process per core, each producing `views_per_proc` views of the whole input with the reference build;
+    returns (views of the whole input per second, wall seconds)"""
     import multiprocessing as mp
-    from oracle import ref
-    if not ref.available():
-        return None
-    info = np.concatenate([ei.T.astype(np.float64), np.ones((ei.shape[1], 1))], axis=1)
-    path = f"/tmp/rlap_b200_info_{os.getpid()}.npy"
-    np.save(path, info)
+    path = f"/tmp/rlap_b200_calls_{os.getpid()}.npy"
+    arr = np.empty(len(calls), dtype=object)
+    for i, c in enumerate(calls):
+        arr[i] = c
+    np.save(path, arr, allow_pickle=True)
     try:
         ctx = mp.get_context("fork")
         with ctx.Pool(procs) as pool:
-            res = pool.map(_ref_worker, [(path, N_NODES, N_NODES // 2, views_per_proc)] * procs, chunksize=1)
+            res = pool.map(_ref_worker, [(path, o_v, o_n, views_per_proc)] * procs, chunksize=1)
         # all workers run concurrently; the slowest one bounds the batch (process start-up and the load of
         # the input file are not charged to the reference)
         wall = max(r[0] for r in res)
@@ -143,52 +218,94 @@ def host_cores():
         return os.cpu_count() or 1
 
 
+def config_dict(wl, o_v, o_n, **extra):
+    d = {"workload": f"{CONFIGS[wl.name]['workload']}, o_v={o_v}, o_n={o_n}", "config": wl.name, "edges": wl.E,
+         "nodes": wl.n}
+    d.update(extra)
+    return d
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import ref
-    ei = make_graph()
+    wl = Workload(args.config)
+    o_v, o_n = args.o_v, args.o_n
     cores = min(host_cores(), 64)
+    if args.config == "C5":
+        cores = min(cores, 2)          # 3 GB of float64 input + one heap node per directed edge per process
+    calls = _ref_calls(wl)
+    single = None
     if not ref.available():
         # oracle port (keyed mode, single thread) stands in when the reference build is absent
         from oracle import port
-        ptr, col, w = port.ingest(ei, None, N_NODES)
+        ei = wl.edge_index_numpy()
         times = []
         for s in range(args.warmup + args.steps):
             t0 = time.perf_counter()
-            port.ingest(ei, None, N_NODES)
-            port.keyed_schur(ptr, col, w, N_NODES // 2, O_V, O_N, seed=s)
+            ptr, col, w = port.ingest(ei, None, wl.n)
+            port.keyed_schur(ptr, col, w, wl.num_remove, o_v, o_n, seed=s, graph_ptr=wl.graph_ptr)
             if s >= args.warmup:
                 times.append(time.perf_counter() - t0)
-        val, kind, cores, sample = 1.0 / statistics.mean(times), "port", 1, "1 view per step, oracle keyed mode"
+        val, kind, cores = wl.units / statistics.mean(times), "port", 1
+        sample = "1 view of the input per step, oracle keyed mode"
         ms = 1e3 * statistics.mean(times)
     else:
+        # the parent loads the library too (the forked workers inherit the mapping): the single-process figure is timed here
+        ref.lib()
+        per = max(1, int(round(0.05 / max(_time_one(calls, o_v, o_n), 1e-6))))   # ~50 ms of work per worker and step at least
+        per = min(per, 2000)
+        if wl.name in ("C4", "C5"):
+            per = 1
+        sp = []
+        for s in range(4 if wl.name not in ("C4", "C5") else 2):
+            t0 = time.perf_counter()
+            for info, n, t in calls:
+                ref.approximate_cholesky(info, n, t, o_v, o_n)
+            sp.append(time.perf_counter() - t0)
+        single = wl.units / statistics.median(sp[1:])
         times = []
         for s in range(args.warmup + args.steps):
-            v, wall = cpu_reference_throughput(ei, cores, 1)
+            v, wall = cpu_reference_throughput(calls, o_v, o_n, cores, per)
             if s >= args.warmup:
                 times.append(wall)
         ms = 1e3 * statistics.mean(times)
-        val, kind = cores / statistics.mean(times), "reference"
-        sample = f"{cores} processes x 1 view per step (unmodified reference C++, Eigen replaced by a container stand-in)"
+        val, kind = wl.units * cores * per / statistics.mean(times), "reference"
+        sample = (f"{cores} processes x {per} view(s) of the input per step (unmodified reference C++, Eigen replaced by a "
+                  f"container stand-in); {len(calls)} call(s) per view")
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C4 arxiv-shaped BA graph n=169343 E~2.37M directed, num_remove=50%, o_v=degree, o_n=asc",
-                   "edges": int(ei.shape[1])},
-        "edges_per_sec": val * int(ei.shape[1]),
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "config": config_dict(wl, o_v, o_n),
+        "edges_per_sec": val / wl.units * wl.E,
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
+                         "single_process_value": single},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
 
 
+def _time_one(calls, o_v, o_n):
+    from oracle import ref
+    t0 = time.perf_counter()
+    for info, n, t in calls:
+        ref.approximate_cholesky(info, n, t, o_v, o_n)
+    return time.perf_counter() - t0
+
+
 # ----------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------
+# kernel launches of one step (counted from the launch code): ingest 12 (count, scatter, rows_warp, rows_block, compact,
+# symmetry, 2 x 3 scan kernels) + export; views: setup_graphs, k_eliminate (ONE cooperative launch for all view groups),
+# combine_groups, emission count pass (prep, scatter, fsort, base, sort_small, 4 x sort_mid, sort_block, sort_big, 2 x 3
+# scan kernels), export_views, k_emit_write
+LAUNCHES_PER_STEP = 13 + 3 + 17 + 1 + 1
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -205,36 +322,34 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    ei_np = make_graph()
-    E = int(ei_np.shape[1])
-    V = args.views
-    t = N_NODES // 2
-    ei_pinned = torch.from_numpy(ei_np).pin_memory()
-    ei_dev = ei_pinned.to(dev)
+    wl = Workload(args.config, device=dev)
+    o_v, o_n = args.o_v, args.o_n
+    E, n, V = wl.E, wl.n, args.views
+    t = wl.num_remove
+    if wl.ei_torch is not None:
+        ei_dev = wl.ei_torch
+        ei_pinned = torch.empty(ei_dev.shape, dtype=torch.int64).pin_memory()
+        ei_pinned.copy_(ei_dev)
+    else:
+        ei_pinned = torch.from_numpy(wl.ei).pin_memory()
+        ei_dev = ei_pinned.to(dev)
     launches = {"n": 0}
     stats_acc = []
 
-    step_wall = []
-
     def step_device(step):
-        step_wall.append(time.perf_counter())
-        g = ops.prepare(ei_dev, None, N_NODES)
-        out, vp, st = ops.schur_views(g, t, O_V, O_N, num_views=V, seed=1234 + step, view_base=rank * V, dtype=None,
+        g = ops.prepare(ei_dev, None, n, graph_ptr=wl.graph_ptr)
+        out, vp, st = ops.schur_views(g, t, o_v, o_n, num_views=V, seed=1234 + step, view_base=rank * V, dtype=None,
                                       return_stats=True)
         stats_acc.append(st)
-        # ingest: 12 kernel launches; views: setup, k_eliminate once per view group (min(V, 32) concurrent cooperative
-        # launches) + combine, prep, base, scatter, sort_warp, 4 x sort_mid, sort_block, sort_big, 2 x 3 scan, export, copy
-        groups = V // ((V + 31) // 32)
-        launches["n"] += 12 + 19 + groups + (1 if groups > 1 else 0)
+        launches["n"] += LAUNCHES_PER_STEP
         return out, vp
 
     # e2e: what a training loop that prefetches views does. Pinned host edge_index in, packed rows out to pinned
     # host buffers; the device->host copy of step i runs on a copy stream while step i+1 computes (two buffer
-    # sets). Every step's H2D and D2H are inside the timed region; at the end the host holds (row, col, w) of every
-    # view. The link is the bottleneck (26 MB per view). Shipping the column pointers instead of `col`
-    # (schur_views(colptr=True) + expand_cols) was measured here too: the D2H drops to 18 MB per view, but rebuilding
-    # col with 8-14 host threads competes with the DMA for this host's memory bandwidth and the step got slower
-    # (32 / 29 ms against 30 ms), so the plain rows are what is timed.
+    # sets). Every step's H2D and D2H are inside the timed region; at the end the host holds the result of every view.
+    #   rows:  (row, col, w) int32/int32/f32 of every view                             12 B per row
+    #   csc:   (row int32, column pointers int32 [V, n + 1]): the unweighted CSC adjacency of every view, what the
+    #          reference's GCL adapters keep (they drop the weights, scripts/augmentor_benchmarks.py:88-96)   4 B per row
     from concurrent.futures import ThreadPoolExecutor
     copy_stream = torch.cuda.Stream(device=dev)
     host_bufs = [dict(), dict()]
@@ -249,76 +364,40 @@ def run_ours(args):
         del keepalive
         return total
 
-    def step_e2e(step):
-        slot = step & 1
-        if pending[slot] is not None:          # the buffers of this slot are still being filled by step - 2
-            pending[slot].result()
-            pending[slot] = None
-        d = ei_pinned.to(dev, non_blocking=True)
-        g = ops.prepare(d, None, N_NODES)
-        (row, col, w), vp = ops.schur_views(g, t, O_V, O_N, num_views=V, seed=1234 + step, view_base=rank * V, dtype=None)
-        total = int(vp[-1])
-        hb = host_bufs[slot]
-        if "row" not in hb or hb["row"].numel() < total:
-            cap = int(total * 1.05)
-            hb["row"] = torch.empty(cap, dtype=torch.int32).pin_memory()
-            hb["col"] = torch.empty(cap, dtype=torch.int32).pin_memory()
-            hb["w"] = torch.empty(cap, dtype=torch.float32).pin_memory()
-        ready = torch.cuda.Event()
-        ready.record()
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(ready)
-            hb["row"][:total].copy_(row, non_blocking=True)
-            hb["col"][:total].copy_(col, non_blocking=True)
-            hb["w"][:total].copy_(w, non_blocking=True)
-            done = torch.cuda.Event()
-            done.record()
-        d2h_bytes["n"] = total * 12
-        pending[slot] = pool.submit(finish, done, total, (row, col, w, g, d))
-        return total
-
-    # the same with per-view column pointers instead of the col array over the link (18 instead of 26 MB per view) and
-    # col rebuilt in the pinned host buffer by host threads; pays off when several GPUs share the host's ingress
-    fill_threads = max(2, min(8, host_cores() // max(world, 1)))
-
-    def finish_colptr(done, hb, vp, total, keepalive):
-        done.synchronize()
-        del keepalive
-        ops.expand_cols(hb["colptr"], vp, out=hb["col"], threads=fill_threads)
-        return total
-
-    def step_e2e_colptr(step):
-        slot = step & 1
-        if pending[slot] is not None:
-            pending[slot].result()
-            pending[slot] = None
-        d = ei_pinned.to(dev, non_blocking=True)
-        g = ops.prepare(d, None, N_NODES)
-        (row, cp, w), vp = ops.schur_views(g, t, O_V, O_N, num_views=V, seed=1234 + step, view_base=rank * V, dtype=None,
-                                           colptr=True)
-        total = int(vp[-1])
-        hb = host_bufs[slot]
-        if "row" not in hb or hb["row"].numel() < total or "colptr" not in hb:
-            cap = int(total * 1.05)
-            hb["row"] = torch.empty(cap, dtype=torch.int32).pin_memory()
-            hb["col"] = torch.empty(cap, dtype=torch.int32).pin_memory()
-            hb["w"] = torch.empty(cap, dtype=torch.float32).pin_memory()
-            hb["colptr"] = torch.empty((V, N_NODES + 1), dtype=torch.int32).pin_memory()
-        ready = torch.cuda.Event()
-        ready.record()
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(ready)
-            hb["row"][:total].copy_(row, non_blocking=True)
-            hb["w"][:total].copy_(w, non_blocking=True)
-            hb["colptr"].copy_(cp, non_blocking=True)
-            done = torch.cuda.Event()
-            done.record()
-        d2h_bytes["n"] = total * 8 + cp.numel() * 4
-        pending[slot] = pool.submit(finish_colptr, done, hb, vp, total, (row, cp, w, g, d))
-        return total
-
-    e2e_mode = args.e2e_mode if args.e2e_mode != "auto" else ("colptr" if world >= 2 else "rows")
-    e2e_step = step_e2e_colptr if e2e_mode == "colptr" else step_e2e
+    def make_e2e(mode):
+        def step_e2e(step):
+            slot = step & 1
+            if pending[slot] is not None:          # the buffers of this slot are still being filled by step - 2
+                pending[slot].result()
+                pending[slot] = None
+            d = ei_pinned.to(dev, non_blocking=True)
+            g = ops.prepare(d, None, n, graph_ptr=wl.graph_ptr)
+            if mode == "rows":
+                (row, col, w), vp = ops.schur_views(g, t, o_v, o_n, num_views=V, seed=1234 + step, view_base=rank * V, dtype=None)
+                parts = {"row": row, "col": col, "w": w}
+            else:
+                (row, cp, w), vp = ops.schur_views(g, t, o_v, o_n, num_views=V, seed=1234 + step, view_base=rank * V,
+                                                   dtype=None, colptr=True, weights=False)
+                parts = {"row": row, "colptr": cp}
+            total = int(vp[-1])
+            hb = host_bufs[slot]
+            nbytes = 0
+            ready = torch.cuda.Event()
+            ready.record()
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(ready)
+                for k, src in parts.items():
+                    flat = src.reshape(-1)
+                    if k not in hb or hb[k].numel() < flat.numel() or hb[k].dtype != flat.dtype:
+                        hb[k] = torch.empty(int(flat.numel() * 1.05) + 16, dtype=flat.dtype).pin_memory()
+                    hb[k][:flat.numel()].copy_(flat, non_blocking=True)
+                    nbytes += flat.numel() * flat.element_size()
+                done = torch.cuda.Event()
+                done.record()
+            d2h_bytes[mode] = nbytes
+            pending[slot] = pool.submit(finish, done, total, (parts, g, d))
+            return total
+        return step_e2e
 
     def drain_e2e():
         for slot in (0, 1):
@@ -331,19 +410,19 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup):
+    def timed(fn, steps, warmup, e2e=False):
         res = None
         for s in range(warmup):
             res = fn(s)       # same allocation pattern as the timed loop: the previous result stays alive during a step
-        if fn is e2e_step:
+        if e2e:
             drain_e2e()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for s in range(steps):
             res = fn(warmup + s)
-        if fn is e2e_step:
-            drain_e2e()          # the last copies (and host rebuilds) are part of the timed region
+        if e2e:
+            drain_e2e()          # the last copies are part of the timed region
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -359,18 +438,31 @@ def run_ours(args):
     launches["n"] = 0
     ms_total, _ = timed(step_device, args.steps, args.warmup)
     timed_stats = stats_acc[args.warmup:]
-    if os.environ.get("BENCH_DEBUG"):
-        print("step starts (ms since first):", [round((x - step_wall[0]) * 1e3, 1) for x in step_wall], file=sys.stderr)
-        print("reserved MB", torch.cuda.memory_reserved() >> 20, "allocated MB", torch.cuda.memory_allocated() >> 20,
-              "num_alloc_retries", torch.cuda.memory_stats().get("num_alloc_retries"),
-              "segments", torch.cuda.memory_stats().get("segment.all.allocated"), file=sys.stderr)
     n_launch = launches["n"] * args.steps // (args.steps + args.warmup)
     clocks = sampler.stop()
-    ms_e2e, total_rows = timed(e2e_step, args.steps, max(args.warmup, 1))
+    ms_e2e, _ = timed(make_e2e("rows"), args.steps, max(args.warmup, 1), e2e=True)
+    host_bufs[0].clear(); host_bufs[1].clear()
+    ms_csc, _ = timed(make_e2e("csc"), args.steps, max(args.warmup, 1), e2e=True)
+    host_bufs[0].clear(); host_bufs[1].clear()
 
+    # single-call latency of the reference's own call shape (one view through ops.approximate_cholesky, device
+    # resident edge_index in, [E',3] float64 out), the figure to put beside the reference's per-call time
+    lat = []
+    if wl.graph_ptr is None and wl.name != "C5":
+        nr = int(t)
+        for s in range(8):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            ops.approximate_cholesky(ei_dev, None, n, nr, o_v, o_n, seed=s)
+            torch.cuda.synchronize()
+            lat.append((time.perf_counter() - t0) * 1e3)
+        lat = lat[3:]
+
+    units = wl.units
     ms_step = ms_total / args.steps
-    value = world * V * args.steps / (ms_total / 1e3)
-    e2e_value = world * V * args.steps / (ms_e2e / 1e3)
+    value = world * V * units * args.steps / (ms_total / 1e3)
+    e2e_value = world * V * units * args.steps / (ms_e2e / 1e3)
+    csc_value = world * V * units * args.steps / (ms_csc / 1e3)
 
     # roofline of the dominant kernel (k_eliminate: ordering + elimination of all views of a step),
     # algorithmic bytes per SURVEY.md §8(d): 8n (ordering) + 8D (adjacency read once) + 24F (fill edges, both
@@ -381,17 +473,17 @@ def run_ours(args):
     D = statistics.mean(s["raw_entries_read"] for s in timed_stats)
     F = statistics.mean(s["fills"] for s in timed_stats)
     rows = statistics.mean(s["rows"] for s in timed_stats)
-    alg_bytes = 8.0 * N_NODES * V + 8.0 * D + 24.0 * F
+    alg_bytes = 8.0 * n * V + 8.0 * D + 24.0 * F
     achieved = alg_bytes / (elim_us * 1e-6) / 1e9
     # whole path, per step: ingest 20E + 4n, then per view 8n + 8D + 24F + 12M + 12E' (M ~ E')
-    path_bytes = 20.0 * E + 4.0 * N_NODES + alg_bytes + 24.0 * rows
+    path_bytes = 20.0 * E + 4.0 * n + alg_bytes + 24.0 * rows
     path_gbs = path_bytes / (ms_step * 1e-3) / 1e9
 
     # measured DRAM traffic of the same kernel from the committed ncu --set full capture (same workload and V)
     traffic = None
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01c_k_eliminate_traffic.json")))
-        if int(tj.get("views_per_launch", 0)) == V:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_k_eliminate_traffic.json")))
+        if int(tj.get("views_per_launch", 0)) == V and tj.get("config") == wl.name and tj.get("o_v") == o_v:
             traffic = float(tj["traffic_bytes_per_launch"])
     except Exception:
         pass
@@ -399,38 +491,40 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": "C4 arxiv-shaped BA graph n=169343 E~2.37M directed, num_remove=50%, o_v=degree, o_n=asc",
-                   "edges": E, "views_per_gpu_per_step": V, "parallelism": f"views sharded over {world} GPU(s)",
-                   "step": "ingest + V views (ordering, elimination, emission), packed int32/int32/f32 rows",
-                   "l2": "per-step working set (~85 MB per view) exceeds the 126 MB L2 for V >= 2"},
-        "edges_per_sec": value * E,
+        "config": config_dict(wl, o_v, o_n, views_per_gpu_per_step=V, parallelism=f"views sharded over {world} GPU(s)",
+                              step="ingest + V views (ordering, elimination, emission), packed int32/int32/f32 rows",
+                              l2="per-step working set exceeds the 126 MB L2" if V * (E * 36 + n * 60) > 126e6 else
+                                 "per-step working set fits the L2; every step writes fresh buffers (seed changes per step)"),
+        "edges_per_sec": value / units * E,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(ei_pinned.numel() * 8),
-                "d2h_bytes_per_step": int(d2h_bytes["n"]), "ms_per_step": ms_e2e / args.steps,
-                "mode": e2e_mode,
-                "api": ("ops.prepare + ops.schur_views from pinned host edge_index; packed rows copied back to pinned host "
-                        "on a copy stream, overlapping the next step (2 buffer sets)") if e2e_mode == "rows" else
-                       ("ops.prepare + ops.schur_views(colptr=True) from pinned host edge_index; rows, weights and per-view "
-                        "column pointers copied back to pinned host on a copy stream, col rebuilt there by "
-                        f"ops.expand_cols with {fill_threads} host threads, both overlapping the next step (2 buffer sets); "
-                        "the host ends with (row, col, w) of every view")},
+                "d2h_bytes_per_step": int(d2h_bytes.get("rows", 0)), "ms_per_step": ms_e2e / args.steps, "mode": "rows",
+                "api": "ops.prepare + ops.schur_views from pinned host edge_index; packed (row, col, w) rows copied back to "
+                       "pinned host on a copy stream, overlapping the next step (2 buffer sets)"},
+        "e2e_csc_unweighted": {"value": csc_value, "unit": UNIT, "d2h_bytes_per_step": int(d2h_bytes.get("csc", 0)),
+                               "ms_per_step": ms_csc / args.steps,
+                               "api": "the same with schur_views(colptr=True, weights=False): the host receives the unweighted "
+                                      "CSC adjacency (row ids + column pointers) of every view, the form the reference's GCL "
+                                      "adapters keep (they drop the weights, scripts/augmentor_benchmarks.py:88-96)"},
+        "single_call_latency_ms": (statistics.median(lat) if lat else None),
         "gpu_launches": int(n_launch),
         "roofline": {"bound": "hbm", "kernel": "k_eliminate", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": elim_us / 1e3,
-                     "launches_per_step": V // ((V + 31) // 32),
-                     "note": "k_eliminate runs as min(V, 32) concurrent cooperative launches (view groups, one grid "
-                             "barrier each); kernel_ms is the CUDA-event time from the first launch to the join of all "
-                             "of them and the bytes are those of all views of the step",
+                     "launches_per_step": 1,
+                     "note": "k_eliminate is ONE cooperative launch per step whose blocks are partitioned into view groups "
+                             "(own barrier each); kernel_ms is its CUDA-event time and the bytes are those of all views of "
+                             "the step",
                      "kernel_share_of_step": elim_us / 1e3 / ms_step,
                      "emit_count_ms": count_us / 1e3,
                      "path": {"algorithmic_bytes_per_step": path_bytes, "achieved": path_gbs, "frac": path_gbs / peak}},
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        # the reference's CPU path on this box's host cores, in a clean subprocess (bounded sample: 1 view per core)
+        # the reference's CPU path on this box's host cores, in a clean subprocess (bounded sample)
         try:
-            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1",
-                                "--warmup", "0"], capture_output=True, text=True, timeout=900)
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--config", args.config,
+                                "--o_v", o_v, "--o_n", o_n, "--steps", "3", "--warmup", "1"],
+                               capture_output=True, text=True, timeout=1500)
             ref_line = json.loads(r.stdout.strip().splitlines()[-1])
             line["cpu_baseline"] = ref_line["cpu_baseline"]
         except Exception as ex:  # pragma: no cover
@@ -447,12 +541,17 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--views", type=int, default=64, help="views per GPU per step")
+    ap.add_argument("--config", default="C4", choices=sorted(CONFIGS))
+    ap.add_argument("--o_v", default=None, choices=["random", "degree", "coarsen"])
+    ap.add_argument("--o_n", default=None, choices=["asc", "desc", "random"])
+    ap.add_argument("--views", type=int, default=None, help="views per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-mode", default="rows", choices=["rows", "colptr", "auto"],
-                    help="what crosses the link in the e2e loop: packed rows, or rows + column pointers (col rebuilt on the host)")
     args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    args.o_v = args.o_v or cfg["o_v"]
+    args.o_n = args.o_n or cfg["o_n"]
+    args.views = args.views or cfg["views"]
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -104,7 +104,8 @@ int rlap_schur_eliminate(int64_t n, int64_t nnz, const int32_t* csr_ptr, const i
  * (row = neighbour, col = surviving vertex, weight), both directions present, original node ids.
  * Either the packed device buffers (out_row/out_col int32, out_w float32) or out_f64 (device
  * double[rows,3], the reference's [E',3] float64 layout, py_api_binder.cc:33-51) or both may be
- * given; pass NULL for the ones not wanted (out_col alone may be NULL too: see rlap_schur_colptr).
+ * given; pass NULL for the ones not wanted (out_col alone may be NULL too: see rlap_schur_colptr; out_w alone may
+ * be NULL for an unweighted view, which is what the reference's GCL adapters keep, scripts/augmentor_benchmarks.py:88-96).
  * Must follow rlap_schur_eliminate on the same workspace.
  * Does not synchronise. */
 int rlap_schur_emit(int64_t n, int64_t nnz, const int32_t* csr_ptr, const int32_t* csr_col, const float* csr_w,
@@ -121,6 +122,20 @@ int rlap_schur_emit(int64_t n, int64_t nnz, const int32_t* csr_ptr, const int32_
  * leaves the host (py_api_binder.cc:54-69). */
 int rlap_schur_colptr(int64_t n, int64_t nnz, int64_t n_views, void* workspace, size_t workspace_bytes,
                       int32_t* colptr, void* stream);
+
+/* ---- survivor compaction + relabelling (the step the reference's adapters run right after the op:
+ * torch.unique over the output's node ids + subgraph(relabel_nodes=True), scripts/augmentor_benchmarks.py:149-155,
+ * scripts/rlap_vc_spectral.py:43-51) ----------------------------------------------------------------------------
+ * rlap_schur_relabel writes newid (device int32[n_views * n + 1], one spare entry): newid[view * n + v] = rank of v
+ * among the vertices of `view` that own at least one output row (ascending id, the order torch.unique returns), -1
+ * for the others; view_nodes (device int64[n_views] or NULL) receives the number of such vertices per view.
+ * rlap_schur_emit_ids is rlap_schur_emit with both ends of every row passed through newid (NULL: plain ids).
+ * Neither synchronises. */
+int rlap_schur_relabel(int64_t n, int64_t nnz, int64_t n_views, void* workspace, size_t workspace_bytes, int32_t* newid,
+                       int64_t* view_nodes, void* stream);
+int rlap_schur_emit_ids(int64_t n, int64_t nnz, const int32_t* csr_ptr, const int32_t* csr_col, const float* csr_w,
+                        int64_t n_views, void* workspace, size_t workspace_bytes, int32_t* out_row, int32_t* out_col,
+                        float* out_w, double* out_f64, const int32_t* newid, void* stream);
 
 /* Forget the results rlap_schur_eliminate left in `workspace`. Call it before the workspace memory is freed or
  * reused: rlap_schur_emit / rlap_schur_colptr refuse a workspace that was released (the library keeps no

@@ -20,7 +20,7 @@ RLAP_ERR_STAR_TOO_LARGE = 6
 EXPORTS = [
     "rlap_status_string", "rlap_last_cuda_error", "rlap_version", "rlap_ingest_workspace_bytes", "rlap_ingest",
     "rlap_schur_workspace_bytes", "rlap_schur_eliminate", "rlap_schur_emit", "rlap_approximate_cholesky_host",
-    "rlap_free_host", "rlap_schur_colptr", "rlap_expand_cols_host", "rlap_schur_release",
+    "rlap_free_host", "rlap_schur_colptr", "rlap_expand_cols_host", "rlap_schur_release", "rlap_schur_relabel", "rlap_schur_emit_ids",
 ]
 
 
@@ -60,6 +60,8 @@ def lib():
     L.rlap_schur_colptr.argtypes = [i64, i64, i64, P, sz, P, P]
     L.rlap_expand_cols_host.argtypes = [P, i64, i64, P, P, ctypes.c_int]
     L.rlap_schur_release.argtypes = [P]
+    L.rlap_schur_relabel.argtypes = [i64, i64, i64, P, sz, P, P, P]
+    L.rlap_schur_emit_ids.argtypes = [i64, i64, P, P, P, i64, P, sz, P, P, P, P, P, P]
     L.rlap_free_host.argtypes = [P]
     L.rlap_free_host.restype = None
     for name in EXPORTS:

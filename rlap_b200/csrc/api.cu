@@ -21,14 +21,17 @@ namespace rlap {
 cudaError_t launch_setup_graphs(int n, int G, const int* gptr, const long long* num_remove, int* gid, int* teff,
                                 cudaStream_t stream);
 cudaError_t eliminate_grid(int* blocks_out);
-cudaError_t launch_eliminate(const SchurParams* groups_dev, const int* block_group_dev, int blocks, int o_v, int o_n,
-                             int flags, cudaStream_t stream);
+cudaError_t launch_eliminate(const SchurParams* groups_host, int K, const int* block_group_host, int blocks, int o_v,
+                             int o_n, int flags, cudaStream_t stream);
+int eliminate_max_groups();
+int eliminate_max_blocks();
 cudaError_t launch_emit_colptr(const SchurParams& P, int* colptr, cudaStream_t stream);
 cudaError_t launch_combine_groups(int K, const int* gctr, const unsigned long long* gstats, int* ctr,
                                   unsigned long long* stats, cudaStream_t stream);
 cudaError_t launch_emit_count(const SchurParams& P, long long* total_dev, cudaStream_t stream);
 cudaError_t launch_emit_write(const SchurParams& P, int* out_row, int* out_col, float* out_w, double* out_f64,
-                              cudaStream_t stream);
+                              const int* newid, cudaStream_t stream);
+cudaError_t launch_relabel(const SchurParams& P, int* newid, long long* base_dev, long long* view_nodes, cudaStream_t stream);
 }  // namespace rlap
 
 using namespace rlap;
@@ -67,7 +70,7 @@ struct Mailbox {
 
 // Streams, events and the mailbox belong to the device that was current when they were created: one set per
 // (host thread, device), created on first use on that device.
-constexpr int MAX_GROUPS = 1024;   // view groups of one call: at most one per block of the launch
+constexpr int MAX_GROUPS = 64;     // view groups of one call (the parameter table of the launch, schur.cu)
 struct ThreadDevice {
     Mailbox mail;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
@@ -143,11 +146,13 @@ const char* rlap_last_cuda_error(void) { return g_last_cuda_error.c_str(); }
 int rlap_version(void) { return 1; }
 
 // ------------------------------------------------------------------------------------------ ingest
-// largest raw row the global-scratch path of the ingest accepts: a row can hold every input entry (duplicates
-// included), so the bound is e, not n
+// largest raw row (duplicates included) the global-scratch path of the ingest accepts: max(n, 4096) entries, never
+// more than e. A vertex with more incident input entries than the graph has vertices is a degenerate multigraph;
+// it is reported as RLAP_ERR_STAR_TOO_LARGE (sizing the NSLOT scratch slots for e entries each would cost 24 e
+// bytes per slot: 24 GB for the products-shaped graph).
 static long long ingest_scratch_cap(long long n, long long e) {
-    (void)n;
-    long long c = e;
+    long long c = n > 4096 ? n : 4096;
+    if (c > e) c = e;
     if (c < CAP_CTA + 1) c = CAP_CTA + 1;
     return c;
 }
@@ -410,12 +415,20 @@ int rlap_schur_eliminate(int64_t n, int64_t nnz, const int32_t* csr_ptr, const i
         // view groups: K groups share the blocks of one cooperative launch
         int blocks = 0;
         CK(eliminate_grid(&blocks));
-        if (blocks > MAX_GROUPS) blocks = MAX_GROUPS;
+        if (blocks > eliminate_max_blocks()) blocks = eliminate_max_blocks();
         if (blocks > MAX_SCRATCH_SLOTS) blocks = MAX_SCRATCH_SLOTS;
-        // every view its own group while there are at least two blocks per view; with more views than that, one
-        // block per group and the views dealt out evenly
+        {
+            // small inputs (the reference's 100-node example, a batch of molecule-sized graphs): about 256 vertices per
+            // block, so that a single small view runs in ONE block - no global barrier, every phase a __syncthreads
+            long long want = (n_views * n + 255) / 256;
+            if (want < 1) want = 1;
+            if (want < blocks) blocks = (int)want;
+        }
+        // every view its own group, up to the number of groups the launch's parameter table holds; more views are
+        // dealt out evenly (elimination time per view does not depend on the split: 98 / 92 / 83 us per arxiv-shaped
+        // view with 64 / 128 / 148 groups, profiles/README.md)
         long long K = n_views;
-        if (K > blocks / 2) K = n_views >= blocks ? blocks : blocks / 2;
+        if (K > eliminate_max_groups()) K = eliminate_max_groups();
 #ifdef RLAP_DEBUG
         if (const char* env = getenv("RLAP_GROUPS")) { K = atoll(env); }
 #endif
@@ -455,9 +468,7 @@ int rlap_schur_eliminate(int64_t n, int64_t nnz, const int32_t* csr_ptr, const i
             slot0 += Q.gblocks < NSLOT ? Q.gblocks : NSLOT;
             for (int b = 0; b < Q.gblocks; b++) block_group[(size_t)(Q.gblock0 + b)] = (int)g;
         }
-        CK(cudaMemcpyAsync(L.gparams, groups.data(), sizeof(SchurParams) * (size_t)K, cudaMemcpyHostToDevice, stream));
-        CK(cudaMemcpyAsync(L.block_group, block_group.data(), sizeof(int) * (size_t)blocks, cudaMemcpyHostToDevice, stream));
-        CK(launch_eliminate(L.gparams, L.block_group, blocks, o_v, o_n, flags, stream));
+        CK(launch_eliminate(groups.data(), (int)K, block_group.data(), blocks, o_v, o_n, flags, stream));
         CK(launch_combine_groups((int)K, L.gctr, L.gstats, P.ctr, P.stats, stream));
     }
 #ifdef RLAP_DEBUG
@@ -532,22 +543,42 @@ int rlap_schur_eliminate(int64_t n, int64_t nnz, const int32_t* csr_ptr, const i
     return RLAP_OK;
 }
 
+static int find_layout(void* workspace, SchurLayout& L) {
+    std::lock_guard<std::mutex> lk(g_layout_mutex);
+    auto it = g_layouts.find(workspace);
+    if (it == g_layouts.end()) return RLAP_ERR_INVALID_ARG;
+    L = it->second;
+    return RLAP_OK;
+}
+
+int rlap_schur_emit_ids(int64_t n, int64_t nnz, const int32_t* csr_ptr, const int32_t* csr_col, const float* csr_w,
+                        int64_t n_views, void* workspace, size_t workspace_bytes, int32_t* out_row, int32_t* out_col,
+                        float* out_w, double* out_f64, const int32_t* newid, void* stream_v) {
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    SchurLayout L;
+    if (find_layout(workspace, L)) return RLAP_ERR_INVALID_ARG;
+    if (L.P.n != n || L.P.nnz != nnz || L.V != n_views || workspace_bytes < L.bytes) return RLAP_ERR_INVALID_ARG;
+    if (L.P.ptr != csr_ptr || L.P.col != csr_col || L.P.w != csr_w) return RLAP_ERR_INVALID_ARG;
+    if ((out_col || out_w) && !out_row) return RLAP_ERR_INVALID_ARG;   // out_col and out_w may be NULL on their own
+    if (!out_row && !out_f64) return RLAP_ERR_INVALID_ARG;
+    CK(launch_emit_write(L.P, out_row, out_col, out_w, out_f64, newid, stream));
+    return RLAP_OK;
+}
+
 int rlap_schur_emit(int64_t n, int64_t nnz, const int32_t* csr_ptr, const int32_t* csr_col, const float* csr_w,
                     int64_t n_views, void* workspace, size_t workspace_bytes, int32_t* out_row, int32_t* out_col,
                     float* out_w, double* out_f64, void* stream_v) {
+    return rlap_schur_emit_ids(n, nnz, csr_ptr, csr_col, csr_w, n_views, workspace, workspace_bytes, out_row, out_col, out_w,
+                               out_f64, nullptr, stream_v);
+}
+
+int rlap_schur_relabel(int64_t n, int64_t nnz, int64_t n_views, void* workspace, size_t workspace_bytes, int32_t* newid,
+                       int64_t* view_nodes, void* stream_v) {
     cudaStream_t stream = (cudaStream_t)stream_v;
     SchurLayout L;
-    {
-        std::lock_guard<std::mutex> lk(g_layout_mutex);
-        auto it = g_layouts.find(workspace);
-        if (it == g_layouts.end()) return RLAP_ERR_INVALID_ARG;
-        L = it->second;
-    }
-    if (L.P.n != n || L.P.nnz != nnz || L.V != n_views || workspace_bytes < L.bytes) return RLAP_ERR_INVALID_ARG;
-    if (L.P.ptr != csr_ptr || L.P.col != csr_col || L.P.w != csr_w) return RLAP_ERR_INVALID_ARG;
-    if ((out_row || out_col || out_w) && !(out_row && out_w)) return RLAP_ERR_INVALID_ARG;   // out_col alone may be NULL
-    if (!out_row && !out_f64) return RLAP_ERR_INVALID_ARG;
-    CK(launch_emit_write(L.P, out_row, out_col, out_w, out_f64, stream));
+    if (find_layout(workspace, L)) return RLAP_ERR_INVALID_ARG;
+    if (L.P.n != n || L.P.nnz != nnz || L.V != n_views || workspace_bytes < L.bytes || !newid) return RLAP_ERR_INVALID_ARG;
+    CK(launch_relabel(L.P, newid, L.viewptr_dev, (long long*)view_nodes, stream));
     return RLAP_OK;
 }
 

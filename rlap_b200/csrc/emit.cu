@@ -303,39 +303,58 @@ constexpr int CAP_BIG = 12288;   // largest segment sorted in the shared memory 
 
 constexpr int FSORT_MAX = 32;    // fills of a clean survivor
 constexpr int FS_LANE = 16;      // fills a single lane sorts in its shared-memory slot
+
+// owner of position p among the 32 ascending row starts a warp holds, one per lane: the last lane whose start is <= p
+// (rows without entries share the start of their successor and are never chosen)
+__device__ __forceinline__ int owner_of(int start, int p) {
+    int lo = 0;
+#pragma unroll
+    for (int step = 16; step > 0; step >>= 1) {
+        const int r = __shfl_sync(RLAP_FULL_MASK, start, (lo + step) & 31);
+        if (lo + step < 32 && r <= p) lo += step;
+    }
+    return lo;
+}
+
 constexpr int FS_NB_MAX = 40;    // longest base row a single lane walks
 
 // Every survivor: sort its fill entries (the tail of its staging segment) by neighbour and look for a multi-edge.
-// A warp owns 32 consecutive vertices and reads their counts in one go. A vertex with at most FS_LANE fills is
-// handled by its lane alone (32 independent chains of loads per warp): insertion sort in a shared-memory slot, then a
-// merge walk over the neighbour ids of its base row for a fill parallel to a base edge. 17..32 fills: the warp sorts
-// them in registers, one vertex after the other. No multi-edge: the sorted fills go back in place and the survivor is
-// "clean" (its row count is its live count; cursor keeps the fill count). Otherwise, or with more than 32 fills, the
-// survivor takes the merge path (cursor = MERGE_PATH) and is listed by size class for the sort kernels.
+// A warp owns 32 consecutive vertices of one view and reads their counts in one go.
+//  * at most FS_LANE fills and a base row of at most FS_NB_MAX entries: the vertex is handled by its lane alone (32
+//    independent chains of loads per warp): insertion sort in a shared-memory slot (two fills to the same neighbour
+//    are a multi-edge), then one merge walk over the neighbour ids of its base row, eight at a time (a fill parallel
+//    to a base edge is a multi-edge);
+//  * otherwise, up to 32 fills: the warp sorts them in registers, one vertex after the other, and every fill looks
+//    its neighbour up in the base row (binary search).
+// No multi-edge: the sorted fills go back in place and the survivor is "clean" (its row count is its live count;
+// cursor keeps the fill count). Otherwise, or with more than 32 fills, the survivor takes the merge path
+// (cursor = MERGE_PATH) and is listed by size class for the sort kernels.
+// (Measured alternatives, profiles/README.md: a warp per vertex for everything 1.9 ms; ranking the staged fills of a
+// batch with all lanes plus one coalesced sweep of the batch's base rows against per-owner filters 1.5 - 1.7 ms -
+// instruction bound on the per-entry owner and fill searches; this version 1.3 ms per 64 arxiv-shaped views.)
 __global__ void __launch_bounds__(256) k_emit_fsort(SchurParams P) {
     __shared__ uint64_t s_slot[8][FS_LANE * 32];
-    const long long VN = (long long)P.V * P.n;
+    const int nbv = (P.n + 31) >> 5;                     // batches per view
+    const long long nbatch = (long long)P.V * nbv;
     const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
     const bool failed = run_failed(P);
     uint64_t* sl = s_slot[threadIdx.x >> 5] + lane;    // element e of this lane: sl[e * 32]
-    for (long long base = gw * 32; base < VN; base += nw * 32) {
-        const long long idx = base + lane;
-        int lv = 0, f = 0, b = 0, nb = 0;
+    for (long long bt = gw; bt < nbatch; bt += nw) {
+        const int view = (int)(bt / nbv), v = (int)(bt % nbv) * 32 + lane;
+        const bool inr = v < P.n;
+        const long long idx = (long long)view * P.n + (inr ? v : P.n - 1);
+        int lv = 0, f = 0;
         long long end = 0;
-        if (idx < VN && !failed) {
+        const int b = __ldg(P.ptr + (inr ? v : P.n)), nb = inr ? __ldg(P.ptr + v + 1) - b : 0;
+        if (inr && !failed) {
             lv = rawcnt_of(P)[idx];
-            if (lv > 0) {
-                f = cursor_of(P)[idx];
-                end = P.rawoff[idx + 1];
-                const int v = (int)(idx % P.n);
-                b = __ldg(P.ptr + v);
-                nb = __ldg(P.ptr + v + 1) - b;
-            }
+            f = cursor_of(P)[idx];
+            end = P.rawoff[idx + 1];
         }
-        if (idx < VN && (lv == 0 || f == 0)) P.outcnt[idx] = lv;      // eliminated / isolated, or no fills at all: clean
+        if (inr && (lv == 0 || f == 0)) P.outcnt[idx] = lv;      // eliminated / isolated, or no fills at all: clean
         int cls = (lv > 0 && f > FSORT_MAX) ? size_class(lv) : -1;
         const bool lanepath = lv > 0 && f > 0 && f <= FS_LANE && nb <= FS_NB_MAX;
         if (lanepath) {
@@ -375,6 +394,7 @@ __global__ void __launch_bounds__(256) k_emit_fsort(SchurParams P) {
                 cls = size_class(lv);
             }
         }
+        __syncwarp();
         unsigned cand = __ballot_sync(RLAP_FULL_MASK, lv > 0 && f > 0 && f <= FSORT_MAX && !lanepath);
         while (cand) {
             const int k = __ffs(cand) - 1;
@@ -387,16 +407,16 @@ __global__ void __launch_bounds__(256) k_emit_fsort(SchurParams P) {
             const bool valid = a != RLAP_PAD_A;
             const uint32_t nbr = a_nbr(a);
             const uint32_t prev = __shfl_up_sync(RLAP_FULL_MASK, nbr, 1);
-            bool dup = valid && lane > 0 && prev == nbr;               // two fills to the same neighbour
+            bool d2 = valid && lane > 0 && prev == nbr;                // two fills to the same neighbour
             if (valid) {                                               // a fill parallel to a base edge of the vertex
                 int lo = 0, hi = knb;
                 while (lo < hi) {
                     const int mid = (lo + hi) >> 1;
                     if ((uint32_t)__ldg(P.col + kb + mid) < nbr) lo = mid + 1; else hi = mid;
                 }
-                dup |= lo < knb && (uint32_t)__ldg(P.col + kb + lo) == nbr;
+                d2 |= lo < knb && (uint32_t)__ldg(P.col + kb + lo) == nbr;
             }
-            if (!__any_sync(RLAP_FULL_MASK, dup)) {
+            if (!__any_sync(RLAP_FULL_MASK, d2)) {
                 if (valid) P.raw[kend - kf + lane] = a;
                 if (lane == k) P.outcnt[idx] = lv;
             } else if (lane == k) {
@@ -416,6 +436,7 @@ __global__ void __launch_bounds__(256) k_emit_fsort(SchurParams P) {
                 if (cls == c) class_list(P, c)[pos0 + __popc(m & lt)] = (unsigned int)idx;
             }
         }
+        __syncwarp();
     }
 }
 
@@ -497,34 +518,40 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 1) k_emit_sort_big(SchurParams 
     }
 }
 
-// Final rows. A warp owns 32 consecutive vertices; their rows are contiguous in the output.
-//  * clean survivor (no multi-edge) of at most WR_LMAX rows: its LANE merges the alive base entries, streamed from
-//    the CSR in neighbour order, with its sorted fills into the warp's shared-memory staging area (32 independent
-//    chains of loads per warp); the warp then writes the staged rows out together, coalesced.
-//  * longer clean survivors: the warp merges by rank (an alive base entry goes to (alive base entries before it) +
-//    (fills with a smaller neighbour), fill i to i + (alive base entries with a smaller neighbour), both from
-//    shuffle binary searches).
+// Final rows. A warp owns 32 consecutive vertices of one view.
+//  * clean survivors (no multi-edge) whose sorted fills fit the warp's shared-memory area: their rows are their alive
+//    base entries and their fills, merged by rank. The base rows of the 32 vertices are one contiguous stretch of the
+//    CSR, which the warp sweeps 32 entries at a time - coalesced, no dependence on the row lengths. An alive base
+//    entry goes to (alive base entries of its row before it) + (fills of its owner with a smaller neighbour: a binary
+//    search in shared memory), and bumps a per-owner histogram over that fill count; fill i then goes to
+//    i + (alive base entries with a smaller neighbour) = i + the histogram's prefix up to i. Nothing is staged or sorted.
+//  * clean survivors beyond the area: the warp merges one vertex at a time by rank (shuffle binary searches).
 //  * merge-path survivors: copy of the merged staging segment.
-constexpr int WR_LMAX = 64;      // longest row a single lane merges
-constexpr int WR_NBMAX = 40;     // longest base row a single lane walks
-constexpr int WR_CAP = 1024;     // staged rows per pass (a pass may run over by one vertex: + WR_LMAX)
+constexpr int WF_CAP = 448;                 // staged fills per warp
+constexpr int WH_STRIDE = FSORT_MAX + 1;    // histogram bins per vertex: 0 .. fills
 constexpr int WR_WARPS = 4;
 __global__ void __launch_bounds__(WR_WARPS * 32) k_emit_write(SchurParams P, int* out_row, int* out_col, float* out_w,
-                                                              double* out_f64) {
-    __shared__ uint64_t s_stage[WR_WARPS][WR_CAP + WR_LMAX];
+                                                              double* out_f64, const int* __restrict__ newid) {
+    __shared__ uint64_t s_fill[WR_WARPS][WF_CAP];
+    __shared__ int s_hist[WR_WARPS][32 * WH_STRIDE];
     if (run_failed(P)) return;
-    const long long VN = (long long)P.V * P.n;
+    const int nbv = (P.n + 31) >> 5;                     // batches per view
+    const long long nbatch = (long long)P.V * nbv;
     const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
     const bool check = (P.flags & 8) != 0;
-    uint64_t* stage = s_stage[threadIdx.x >> 5];
+    uint64_t* sfill = s_fill[threadIdx.x >> 5];
+    int* shist = s_hist[threadIdx.x >> 5];
+    // newid (optional): compact ids of the view's vertices (rlap_schur_relabel), applied to both ends of every row
+    const int* nid = nullptr;
     auto put = [&](long long w, uint32_t r, int c, float wt) {
+        if (nid) { r = (uint32_t)__ldg(nid + r); c = __ldg(nid + c); }
         if (out_row) {
             __stcs(out_row + w, (int)r);
             if (out_col) __stcs(out_col + w, c);      // NULL: the caller rebuilds the columns from the column pointers
-            __stcs(out_w + w, wt);
+            if (out_w) __stcs(out_w + w, wt);         // NULL: an unweighted view
         }
         if (out_f64) {
             out_f64[w * 3 + 0] = (double)r;
@@ -536,105 +563,117 @@ __global__ void __launch_bounds__(WR_WARPS * 32) k_emit_write(SchurParams P, int
         atomicAdd(P.stats + 7, 1ull);
         atomicMax(P.stats + 6, ((unsigned long long)(unsigned)vidx << 32) | ((unsigned long long)(unsigned)(got & 0xffff) << 16) | (unsigned)(want & 0xffff));
     };
-    for (long long base = gw * 32; base < VN; base += nw * 32) {
-        const long long idx = base + lane;
-        int L = 0, f = 0, b = 0, nb = 0, v = 0;
+    for (long long bt = gw; bt < nbatch; bt += nw) {
+        const int view = (int)(bt / nbv), v = (int)(bt % nbv) * 32 + lane;
+        const bool inr = v < P.n;
+        const long long idx = (long long)view * P.n + (inr ? v : P.n - 1);
+        const size_t vb = (size_t)view * (size_t)P.n;
+        nid = newid ? newid + vb : nullptr;
+        const int b = __ldg(P.ptr + (inr ? v : P.n)), nb = inr ? __ldg(P.ptr + v + 1) - b : 0;
+        int L = 0, f = 0;
         long long dst = 0, src = 0, end = 0;
-        if (idx < VN) {
+        if (inr) {
             L = P.outcnt[idx];
-            if (L > 0) {
-                f = cursor_of(P)[idx];
-                dst = P.outoff[idx];
-                src = P.rawoff[idx];
-                end = P.rawoff[idx + 1];
-                v = (int)(idx % P.n);
-                b = __ldg(P.ptr + v);
-                nb = __ldg(P.ptr + v + 1) - b;
-            }
+            f = cursor_of(P)[idx];
+            dst = P.outoff[idx];
+            src = P.rawoff[idx];
+            end = P.rawoff[idx + 1];
         }
-        // ---- lane tier
-        const bool staged = L > 0 && f != MERGE_PATH && L <= WR_LMAX && nb <= WR_NBMAX;
-        const int Ls = staged ? L : 0;
-        int srel = Ls;   // exclusive prefix of the staged row counts
+        if (!__any_sync(RLAP_FULL_MASK, L > 0)) continue;
+        // ---- flat tier: clean survivors, as many as the fill area holds (in lane order)
+        const bool clean = L > 0 && f != MERGE_PATH;
+        int foff = clean ? f : 0;    // exclusive prefix of the fill counts of the clean survivors
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            const int t = __shfl_up_sync(RLAP_FULL_MASK, srel, d);
-            if (lane >= d) srel += t;
+            const int t = __shfl_up_sync(RLAP_FULL_MASK, foff, d);
+            if (lane >= d) foff += t;
         }
-        const int stot = __shfl_sync(RLAP_FULL_MASK, srel, 31);
-        srel -= Ls;
-        int s0 = 0;
-        for (int pass = 0; pass * WR_CAP < stot; pass++) {
-            const bool mine = staged && srel / WR_CAP == pass;
-            if (mine) {
-                uint64_t* st = stage + (srel - pass * WR_CAP);
-                const size_t vb = (size_t)(idx - v);
-                const uint64_t* fp = P.raw + (end - f);   // sorted fills
-                // the fills are parked at the end of this lane's staging span and merged forward in place: the output
-                // position (base entries emitted + fills emitted) never passes the next unread fill
-                uint64_t* sf = st + (L - f);
-#pragma unroll 4
-                for (int i = 0; i < f; i++) sf[i] = fp[i];
-                int r = 0, i = 0;
-                uint32_t nfn = f > 0 ? a_nbr(sf[0]) : 0xffffffffu;   // no fill left: the largest id, never "smaller"
-                for (int p0 = 0; p0 < nb; p0 += 8) {
-                    uint32_t c8[8];
-                    float w8[8];
-                    uint8_t s8[8];
+        const bool flat = clean && foff <= WF_CAP;      // foff is still inclusive here
+        foff -= clean ? f : 0;
+        const int ff = flat ? f : 0;
+        const int ftot = __reduce_max_sync(RLAP_FULL_MASK, flat ? foff + f : 0);
+        // fills of the flat survivors -> shared memory, all lanes busy whatever the split between vertices
+        for (int t0 = 0; t0 < ftot; t0 += 32) {      // uniform trip count: the searches are warp-wide shuffles
+            const int t = t0 + lane;
+            // owner of staged fill t: the last lane whose prefix is <= t (a lane that stages nothing shares the prefix of
+            // its successor, and the search resolves equals to the last one)
+            int lo = 0;
 #pragma unroll
-                    for (int k = 0; k < 8; k++) {
-                        const bool in = p0 + k < nb;
-                        c8[k] = in ? (uint32_t)__ldg(P.col + b + p0 + k) : 0xffffffffu;
-                        w8[k] = in ? __ldg(P.w + b + p0 + k) : 0.f;
+            for (int step = 16; step > 0; step >>= 1) {
+                const int r = __shfl_sync(RLAP_FULL_MASK, foff, (lo + step) & 31);
+                if (lo + step < 32 && r <= t) lo += step;
+            }
+            const long long oend = __shfl_sync(RLAP_FULL_MASK, end, lo);
+            const int of = __shfl_sync(RLAP_FULL_MASK, ff, lo), oo = __shfl_sync(RLAP_FULL_MASK, foff, lo);
+            if (t < ftot) sfill[t] = __ldcs((const unsigned long long*)P.raw + (oend - of + (t - oo)));
+        }
+        for (int t = lane; t < 32 * WH_STRIDE; t += 32) shist[t] = 0;
+        __syncwarp();
+        if (__any_sync(RLAP_FULL_MASK, flat)) {
+            const int p_begin = __shfl_sync(RLAP_FULL_MASK, b, 0);
+            const int p_end = __shfl_sync(RLAP_FULL_MASK, b + nb, 31);
+            int run = 0;       // alive base entries of flat survivors seen so far
+            int rs = 0;        // value of `run` at the start of this lane's row
+            for (int p0 = p_begin; p0 < p_end; p0 += 32) {
+                const int p = p0 + lane;
+                const bool in = p < p_end;
+                uint32_t c = 0xffffffffu;
+                float w = 0.f;
+                if (in) { c = (uint32_t)__ldg(P.col + p); w = __ldg(P.w + p); }
+                const int o = owner_of(b, p);
+                const bool oflat = __shfl_sync(RLAP_FULL_MASK, (int)flat, o) != 0;
+                const bool alive = in && oflat && P.state[vb + c] != 2;
+                const unsigned mask = __ballot_sync(RLAP_FULL_MASK, alive);
+                // rows that start inside this step note how many alive entries came before them
+                if (b >= p0 && b < p0 + 32) rs = run + __popc(mask & ((1u << (b - p0)) - 1u));
+                const int ors = __shfl_sync(RLAP_FULL_MASK, rs, o);
+                const int of = __shfl_sync(RLAP_FULL_MASK, ff, o), oo = __shfl_sync(RLAP_FULL_MASK, foff, o);
+                const long long odst = __shfl_sync(RLAP_FULL_MASK, dst, o);
+                if (alive) {
+                    int lo = 0, hi = of;     // fills of the owner with a smaller neighbour
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        if (a_nbr(sfill[oo + mid]) < c) lo = mid + 1; else hi = mid;
                     }
-#pragma unroll
-                    for (int k = 0; k < 8; k++) s8[k] = (c8[k] != 0xffffffffu) ? P.state[vb + c8[k]] : (uint8_t)2;
-#pragma unroll
-                    for (int k = 0; k < 8; k++) {
-                        if (s8[k] != 2) {
-                            while (nfn < c8[k]) {
-                                if (r < L) st[r] = sf[i];
-                                r++; i++;
-                                nfn = i < f ? a_nbr(sf[i]) : 0xffffffffu;
-                            }
-                            if (r < L) st[r] = pack_a(c8[k], w8[k]);
-                            r++;
-                        }
-                    }
+                    put(odst + (run + __popc(mask & lt) - ors) + lo, c, (int)(bt % nbv) * 32 + o, w);
+                    atomicAdd(shist + o * WH_STRIDE + lo, 1);
                 }
-                r += f - i;   // the remaining fills are already in place
-                if (check && r != L) mismatch(idx, r, L);
+                run += __popc(mask);
             }
             __syncwarp();
-            // staged rows [s0, s1) of this pass -> output, coalesced; the owner of staged row s is the last lane whose
-            // prefix is <= s (lanes that stage nothing share the prefix of their successor)
-            const int s1 = __reduce_max_sync(RLAP_FULL_MASK, mine ? srel + Ls : s0);
-            for (int sb = s0; sb < s1; sb += 32) {
-                const int sidx = sb + lane;
+            // prefix of every owner's histogram: entry i = alive base entries with fewer than or exactly i smaller fills,
+            // i.e. the base entries that precede fill i
+            if (flat) {
+                int acc = 0;
+                for (int i = 0; i <= f; i++) { acc += shist[lane * WH_STRIDE + i]; shist[lane * WH_STRIDE + i] = acc; }
+                if (check && acc + f != L) mismatch(idx, acc + f, L);
+            }
+            __syncwarp();
+            for (int t0 = 0; t0 < ftot; t0 += 32) {
+                const int t = t0 + lane;
                 int lo = 0;
 #pragma unroll
                 for (int step = 16; step > 0; step >>= 1) {
-                    const int r = __shfl_sync(RLAP_FULL_MASK, srel, (lo + step) & 31);
-                    if (lo + step < 32 && r <= sidx) lo += step;
+                    const int r = __shfl_sync(RLAP_FULL_MASK, foff, (lo + step) & 31);
+                    if (lo + step < 32 && r <= t) lo += step;
                 }
+                const int oo = __shfl_sync(RLAP_FULL_MASK, foff, lo);
                 const long long odst = __shfl_sync(RLAP_FULL_MASK, dst, lo);
-                const int osrel = __shfl_sync(RLAP_FULL_MASK, srel, lo);
-                const int ov = __shfl_sync(RLAP_FULL_MASK, v, lo);
-                if (sidx < s1) {
-                    const uint64_t a = stage[sidx - pass * WR_CAP];
-                    put(odst + (sidx - osrel), a_nbr(a), ov, a_w(a));
+                if (t < ftot) {
+                    const int i = t - oo;
+                    const uint64_t a = sfill[t];
+                    put(odst + i + shist[lo * WH_STRIDE + i], a_nbr(a), (int)(bt % nbv) * 32 + lo, a_w(a));
                 }
             }
-            s0 = s1;
             __syncwarp();
         }
-        // ---- cooperative tier: the survivors the lanes did not take
-        unsigned todo = __ballot_sync(RLAP_FULL_MASK, L > 0 && !staged);
+        // ---- cooperative tier: the survivors the flat sweep did not take
+        unsigned todo = __ballot_sync(RLAP_FULL_MASK, L > 0 && !flat);
         while (todo) {
             const int k = __ffs(todo) - 1;
             todo &= todo - 1;
             const int kL = __shfl_sync(RLAP_FULL_MASK, L, k), kf = __shfl_sync(RLAP_FULL_MASK, f, k);
-            const int kv = __shfl_sync(RLAP_FULL_MASK, v, k);
+            const int kv = (int)(bt % nbv) * 32 + k;
             const long long kdst = __shfl_sync(RLAP_FULL_MASK, dst, k);
             if (kf == MERGE_PATH) {
                 const long long ksrc = __shfl_sync(RLAP_FULL_MASK, src, k);
@@ -646,7 +685,6 @@ __global__ void __launch_bounds__(WR_WARPS * 32) k_emit_write(SchurParams P, int
             }
             const int kb = __shfl_sync(RLAP_FULL_MASK, b, k), knb = __shfl_sync(RLAP_FULL_MASK, nb, k);
             const long long kend = __shfl_sync(RLAP_FULL_MASK, end, k);
-            const size_t vb = (size_t)(base + k - kv);
             // sorted fills, one per lane; a lane without one holds the largest id, so it never counts as "smaller"
             const uint64_t fa = lane < kf ? __ldcs((const unsigned long long*)P.raw + kend - kf + lane) : RLAP_PAD_A;
             const uint32_t fnbr = a_nbr(fa);
@@ -684,9 +722,41 @@ __global__ void __launch_bounds__(WR_WARPS * 32) k_emit_write(SchurParams P, int
                 run += __popc(mask);
             }
             if (lane < kf) put(kdst + lane + cb, fnbr, kv, a_w(fa));
-            if (check && lane == 0 && run + kf != kL) mismatch(base + k, run + kf, kL);
+            if (check && lane == 0 && run + kf != kL) mismatch((long long)view * P.n + kv, run + kf, kL);
         }
     }
+}
+
+// ---- survivor compaction + relabelling (the step the reference's adapters run after the op: torch.unique of the
+// output's node ids + subgraph(relabel_nodes=True), scripts/augmentor_benchmarks.py:149-155, rlap_vc_spectral.py:43-51)
+// newid[view * n + v] = rank of v among the vertices of the view that have at least one row, -1 for the others
+__global__ void k_relabel_flags(SchurParams P) {
+    const long long VN = (long long)P.V * P.n;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < VN) rawcnt_of(P)[idx] = P.outcnt[idx] > 0 ? 1 : 0;
+}
+__global__ void k_relabel_base(const int* scan, long long n, long long V, long long* base) {
+    const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v <= V) base[v] = scan[v * n];
+}
+__global__ void k_relabel_final(SchurParams P, int* newid, const long long* base, long long* view_nodes) {
+    const long long VN = (long long)P.V * P.n;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < VN) {
+        const long long view = idx / P.n;
+        newid[idx] = rawcnt_of(P)[idx] ? (int)(newid[idx] - base[view]) : -1;
+    }
+    if (view_nodes && idx < P.V) view_nodes[idx] = base[idx + 1] - base[idx];
+}
+
+cudaError_t launch_relabel(const SchurParams& P, int* newid, long long* base_dev, long long* view_nodes, cudaStream_t stream) {
+    const long long VN = (long long)P.V * P.n;
+    k_relabel_flags<<<(unsigned)((VN + 255) / 256), 256, 0, stream>>>(P);
+    cudaError_t e = launch_exclusive_scan<int>(P.blk, VN, newid, P.blocksum, nullptr, stream);
+    if (e != cudaSuccess) return e;
+    k_relabel_base<<<(unsigned)((P.V + 1 + 127) / 128), 128, 0, stream>>>(newid, P.n, P.V, base_dev);
+    k_relabel_final<<<(unsigned)((VN + 255) / 256), 256, 0, stream>>>(P, newid, base_dev, view_nodes);
+    return cudaGetLastError();
 }
 
 // column pointers of every view: colptr[view * (n + 1) + v] = rows of `view` that precede column v (v = n: all rows)
@@ -702,6 +772,20 @@ __global__ void k_emit_colptr(SchurParams P, int* colptr) {
 // host-side launchers
 // ---------------------------------------------------------------------------------------------
 cudaError_t eliminate_grid(int* blocks_out);
+
+// -DRLAP_DEBUG with RLAP_DEBUG_SYNC=1: synchronise after every emission kernel and name the one that failed
+#ifdef RLAP_DEBUG
+#include <stdio.h>
+#define DBG_SYNC(name)                                                                        \
+    do {                                                                                      \
+        if (getenv("RLAP_DEBUG_SYNC")) {                                                      \
+            cudaError_t _de = cudaStreamSynchronize(stream);                                  \
+            if (_de != cudaSuccess) { fprintf(stderr, "rlap debug: %s failed: %s\n", name, cudaGetErrorString(_de)); return _de; } \
+        }                                                                                     \
+    } while (0)
+#else
+#define DBG_SYNC(name) do {} while (0)
+#endif
 
 cudaError_t launch_emit_count(const SchurParams& P, long long* total_dev, cudaStream_t stream) {
     const size_t smem = (size_t)3 * CAP_CTA * sizeof(uint64_t);
@@ -721,6 +805,7 @@ cudaError_t launch_emit_count(const SchurParams& P, long long* total_dev, cudaSt
     cudaError_t e = cudaMemsetAsync(P.ctr + CTR_EMIT_C0, 0, N_CLASS * sizeof(int), stream);
     if (e != cudaSuccess) return e;
     k_emit_prep<<<(unsigned)((VN + 255) / 256), 256, 0, stream>>>(P);
+    DBG_SYNC("k_emit_prep");
     e = launch_exclusive_scan<long long>(P.blk, VN, P.rawoff, P.blocksum, nullptr, stream);
     if (e != cudaSuccess) return e;
     {
@@ -729,14 +814,17 @@ cudaError_t launch_emit_count(const SchurParams& P, long long* total_dev, cudaSt
         if (bx < 1) bx = 1;
         if (bx > 148 * 8) bx = 148 * 8;
         k_emit_scatter<<<dim3((unsigned)bx, (unsigned)P.V), 256, 0, stream>>>(P);
-        bx = (VN + 255) / 256;            // one warp per 32 vertices
+        DBG_SYNC("k_emit_scatter");
+        bx = ((long long)P.V * ((P.n + 31) / 32) + 7) / 8;   // one warp per 32 vertices of a view
         if (bx < 1) bx = 1;
         if (bx > 148 * 16) bx = 148 * 16;
         k_emit_fsort<<<(unsigned)bx, 256, 0, stream>>>(P);
+        DBG_SYNC("k_emit_fsort");
         bx = (VN / 4 * 32 + 255) / 256;   // one 8-lane tile per vertex
         if (bx < 1) bx = 1;
         if (bx > 148 * 16) bx = 148 * 16;
         k_emit_base<<<(unsigned)bx, 256, 0, stream>>>(P);
+        DBG_SYNC("k_emit_base");
     }
     int blocks = 0;
     e = eliminate_grid(&blocks);
@@ -748,6 +836,7 @@ cudaError_t launch_emit_count(const SchurParams& P, long long* total_dev, cudaSt
     k_emit_sort_mid<16><<<148 * 4, 256, 0, stream>>>(P);
     k_emit_sort_block<<<blocks, BLOCK_THREADS, smem, stream>>>(P);
     k_emit_sort_big<<<blocks / 2, BLOCK_THREADS, smem_big, stream>>>(P);
+    DBG_SYNC("k_emit_sort_*");
     return launch_exclusive_scan<long long>(P.outcnt, VN, P.outoff, P.blocksum, total_dev, stream);
 }
 
@@ -758,12 +847,12 @@ cudaError_t launch_emit_colptr(const SchurParams& P, int* colptr, cudaStream_t s
 }
 
 cudaError_t launch_emit_write(const SchurParams& P, int* out_row, int* out_col, float* out_w, double* out_f64,
-                              cudaStream_t stream) {
-    const long long VN = (long long)P.V * P.n;
-    long long bx = (VN + 32 * WR_WARPS - 1) / (32 * WR_WARPS);  // one warp per 32 vertices
+                              const int* newid, cudaStream_t stream) {
+    long long bx = ((long long)P.V * ((P.n + 31) / 32) + WR_WARPS - 1) / WR_WARPS;  // one warp per 32 vertices of a view
     if (bx < 1) bx = 1;
-    if (bx > 148 * 24) bx = 148 * 24;
-    k_emit_write<<<(unsigned)bx, WR_WARPS * 32, 0, stream>>>(P, out_row, out_col, out_w, out_f64);
+    if (bx > 148 * 32) bx = 148 * 32;
+    k_emit_write<<<(unsigned)bx, WR_WARPS * 32, 0, stream>>>(P, out_row, out_col, out_w, out_f64, newid);
+    DBG_SYNC("k_emit_write");
     return cudaGetLastError();
 }
 

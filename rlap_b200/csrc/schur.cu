@@ -1031,11 +1031,25 @@ __device__ __forceinline__ void group_sync(int* bar, int nblocks) {
     }
 }
 
-// One cooperative launch serves every view group of a call: block b works on the parameter block garr[block_group[b]].
+// One cooperative launch serves every view group of a call: block b works on the parameter block tab.g[tab.bg[b]].
+// The table travels as a kernel parameter (22 KB of the 32 KB parameter space), so every field of every group is a
+// constant-bank operand; a table in global memory costs the persistent kernel 160 B more spill stores and 0.9 ms per
+// 64 arxiv-shaped views (measured, profiles/README.md).
+constexpr int TAB_GROUPS = 64;
+constexpr int TAB_BLOCKS = 512;
 template <int OV, int ON, bool FULL>
-__global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(const ModeParams<OV, ON, FULL>* __restrict__ garr,
-                                                                const int* __restrict__ block_group) {
-    const ModeParams<OV, ON, FULL>& P = garr[__ldg(block_group + blockIdx.x)];
+struct GroupTable {
+    ModeParams<OV, ON, FULL> g[TAB_GROUPS];
+    unsigned short bg[TAB_BLOCKS];
+};
+struct GroupTableRaw {               // what the host fills: same layout
+    SchurParams g[TAB_GROUPS];
+    unsigned short bg[TAB_BLOCKS];
+};
+
+template <int OV, int ON, bool FULL>
+__global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(const __grid_constant__ GroupTable<OV, ON, FULL> tab) {
+    const ModeParams<OV, ON, FULL>& P = tab.g[tab.bg[blockIdx.x]];
     extern __shared__ __align__(16) uint64_t smem[];
     __shared__ CtaScratch cs;
     __shared__ int s_next, s_nsel;
@@ -1820,9 +1834,16 @@ cudaError_t eliminate_grid(int* blocks_out) {
     return cudaSuccess;
 }
 
-cudaError_t launch_eliminate(const SchurParams* groups_dev, const int* block_group_dev, int blocks, int o_v, int o_n,
-                             int flags, cudaStream_t stream) {
-    void* args[] = {(void*)&groups_dev, (void*)&block_group_dev};
+int eliminate_max_groups() { return TAB_GROUPS; }
+int eliminate_max_blocks() { return TAB_BLOCKS; }
+
+cudaError_t launch_eliminate(const SchurParams* groups_host, int K, const int* block_group_host, int blocks, int o_v,
+                             int o_n, int flags, cudaStream_t stream) {
+    if (K < 1 || K > TAB_GROUPS || blocks < 1 || blocks > TAB_BLOCKS) return cudaErrorInvalidValue;
+    static thread_local GroupTableRaw tab;     // copied into the launch's parameter buffer by the launch call
+    for (int g = 0; g < K; g++) tab.g[g] = groups_host[g];
+    for (int b = 0; b < blocks; b++) tab.bg[b] = (unsigned short)block_group_host[b];
+    void* args[] = {(void*)&tab};
     const int m = mode_index(o_v, o_n, (flags & 1) != 0);
     return cudaLaunchCooperativeKernel(mode_kernel(m), dim3(blocks), dim3(BLOCK_THREADS), args,
                                        eliminate_smem_bytes(mode_needs_keys(m)), stream);

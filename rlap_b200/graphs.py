@@ -96,3 +96,46 @@ def proteins_like_batch(n_graphs: int = 1113, mean_nodes: float = 39.06, seed: i
         ei = barabasi_albert(int(sizes[g]), 2, seed=seed * 1000003 + g)
         parts.append(ei + ptr[g])
     return np.concatenate(parts, axis=1), ptr
+
+
+def sbm_torch(n: int, n_blocks: int, n_undirected: int, p_ratio: float = 10.0, seed: int = 0, device="cuda"):
+    """The same stochastic block model as `sbm`, generated with torch on `device` (the ogbn-products-shaped graph of
+    C5 has 61.9 M undirected edges: seconds on a GPU, minutes in numpy). Returns a torch int64 edge_index [2, 2 *
+    n_undirected] on `device`: directed, symmetric, duplicate free, sorted by (row, col). Not the same edges as `sbm`
+    for the same seed (different random streams)."""
+    import torch
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed)
+    dev = torch.device(device)
+    block = (torch.arange(n, device=dev, dtype=torch.int64) * n_blocks) // n
+    sizes = torch.bincount(block, minlength=n_blocks)
+    starts = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), torch.cumsum(sizes, 0)])
+    pb = (sizes * (sizes - 1) / 2.0).double()
+    pairs_in = float(pb.sum())
+    pairs_all = n * (n - 1) / 2.0
+    w_in = p_ratio * pairs_in
+    frac_in = w_in / (w_in + (pairs_all - pairs_in))
+    keys = torch.empty(0, dtype=torch.int64, device=dev)
+    while keys.numel() < n_undirected:
+        need = n_undirected - keys.numel()
+        k = int(need * 1.2) + 16
+        n_in = int(round(k * frac_in))
+        b = torch.multinomial((pb / pb.sum()).float(), n_in, replacement=True, generator=gen)
+        u = starts[b] + (torch.rand(n_in, device=dev, generator=gen, dtype=torch.float64) * sizes[b]).long()
+        v = starts[b] + (torch.rand(n_in, device=dev, generator=gen, dtype=torch.float64) * sizes[b]).long()
+        uo = torch.randint(0, n, (k - n_in,), device=dev, generator=gen)
+        vo = torch.randint(0, n, (k - n_in,), device=dev, generator=gen)
+        ok = block[uo] != block[vo]
+        u = torch.cat([u, uo[ok]])
+        v = torch.cat([v, vo[ok]])
+        ok = u != v
+        lo, hi = torch.minimum(u[ok], v[ok]), torch.maximum(u[ok], v[ok])
+        new = torch.unique(lo * n + hi)
+        if keys.numel():
+            new = new[~torch.isin(new, keys)]
+        if new.numel() > need:
+            new = new[torch.randperm(new.numel(), device=dev, generator=gen)[:need]]
+        keys = torch.unique(torch.cat([keys, new]))
+    lo, hi = keys // n, keys % n
+    both = torch.sort(torch.cat([lo * n + hi, hi * n + lo])).values
+    return torch.stack([both // n, both % n])

@@ -111,7 +111,7 @@ def prepare(edge_index: Tensor, edge_weights: Optional[Tensor], num_nodes: int,
 def schur_views(graph: Graph, num_remove, o_v: str, o_n: str, num_views: int = 1, seed: Optional[int] = None,
                 view_base: int = 0, full_clique: bool = False, shared_order: bool = False, dtype=torch.float64,
                 pool_cap: int = 0, scratch_cap: int = 0, return_stats: bool = False, colptr: bool = False,
-                check_live: bool = False):
+                check_live: bool = False, weights: bool = True):
     """num_views independent randomized Schur-complement views of `graph`.
 
     Returns (edge_info, view_ptr): edge_info is [sum E'_v, 3] (row, col, weight) of `dtype`
@@ -120,7 +120,8 @@ def schur_views(graph: Graph, num_remove, o_v: str, o_n: str, num_views: int = 1
     ((row int32, col int32, w float32), view_ptr). num_remove: int or one value per graph.
     colptr=True (with dtype=None): the `col` array is replaced by the per-view column pointers, an int32 tensor
     [num_views, n + 1] (rows of a view are sorted by column, so col is implied; `expand_cols` rebuilds it on the
-    host) - a third less to move for consumers behind a PCIe link."""
+    host) - a third less to move for consumers behind a PCIe link. weights=False (with dtype=None): no weight array
+    is written (w is None): the unweighted view the reference's GCL adapters keep."""
     assert o_v in _O_V
     assert o_n in _O_N
     L = _native.lib()
@@ -164,7 +165,7 @@ def schur_views(graph: Graph, num_remove, o_v: str, o_n: str, num_views: int = 1
         view_ptr = torch.from_numpy(np.concatenate([[0], np.cumsum(rows)]).astype(np.int64))
         if dtype is None:
             orow = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
-            ow = torch.empty(max(total, 1), dtype=torch.float32, device=dev)
+            ow = torch.empty(max(total, 1), dtype=torch.float32, device=dev) if weights else None
             if colptr:
                 ocp = torch.empty((V, graph.n + 1), dtype=torch.int32, device=dev)
                 _native.check(L.rlap_schur_colptr(graph.n, graph.nnz, V, ws.data_ptr(), wsb.value, ocp.data_ptr(), stream),
@@ -173,8 +174,9 @@ def schur_views(graph: Graph, num_remove, o_v: str, o_n: str, num_views: int = 1
                 ocol = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
             _native.check(L.rlap_schur_emit(graph.n, graph.nnz, graph.ptr.data_ptr(), graph.col.data_ptr(),
                                             graph.w.data_ptr(), V, ws.data_ptr(), wsb.value, orow.data_ptr(),
-                                            0 if colptr else ocol.data_ptr(), ow.data_ptr(), 0, stream), "schur_emit")
-            out = (orow[:total], ocp if colptr else ocol[:total], ow[:total])
+                                            0 if colptr else ocol.data_ptr(), ow.data_ptr() if weights else 0, 0, stream),
+                          "schur_emit")
+            out = (orow[:total], ocp if colptr else ocol[:total], ow[:total] if weights else None)
         else:
             o64 = torch.empty((max(total, 1), 3), dtype=torch.float64, device=dev)
             _native.check(L.rlap_schur_emit(graph.n, graph.nnz, graph.ptr.data_ptr(), graph.col.data_ptr(),

@@ -274,3 +274,95 @@ def test_column_pointer_output_matches_packed_rows():
         assert cp.shape == (5, n + 1) and cp.dtype == torch.int32
         col2 = ops.expand_cols(cp.cpu(), vp2, threads=4)
         assert torch.equal(col.cpu()[: int(vp[-1])], col2), name
+
+
+@pytest.mark.gpu
+def test_batched_dispatcher_op(oracle_port):
+    """torch.ops.extension_cpp.approximate_cholesky_batched: the views of every graph of a batch in one
+    dispatcher call, bit-exact against the oracle"""
+    import rlap_b200
+    from rlap_b200 import graphs
+    assert rlap_b200.register_torch_op()
+    ei, ptr = graphs.proteins_like_batch(24, seed=7)
+    n = int(ptr[-1])
+    nr = np.diff(ptr) // 2
+    out, vp = torch.ops.extension_cpp.approximate_cholesky_batched.default(
+        edge_index=torch.from_numpy(ei).cuda(), edge_weight=None, graph_ptr=torch.from_numpy(ptr),
+        num_remove=torch.from_numpy(nr), o_v="degree", o_n="desc", num_views=2, seed=77)
+    assert out.dtype == torch.double and out.is_cuda and vp.shape[0] == 3
+    optr, ocol, ow = oracle_port.ingest(ei, None, n)
+    o = out.cpu().numpy()
+    for v in range(2):
+        r0, c0, w0 = oracle_port.keyed_schur(optr, ocol, ow, nr, "degree", "desc", seed=77, view=v, graph_ptr=ptr)
+        s, e = int(vp[v]), int(vp[v + 1])
+        assert np.array_equal(o[s:e, 0], r0) and np.array_equal(o[s:e, 1], c0)
+        assert np.array_equal(o[s:e, 2].astype(np.float32).view(np.uint32), w0.view(np.uint32))
+
+
+@pytest.mark.gpu
+def test_two_host_threads_two_streams(oracle_port):
+    """Threading row of the boundary: calls issued concurrently from two host threads, each on its own
+    CUDA stream, return what the same calls return one after the other"""
+    import threading
+    import rlap_b200
+    ei = util.small_cases()[2][1]          # Cora-shaped SBM
+    n, t = 2708, 812
+    optr, ocol, ow = oracle_port.ingest(ei, None, n)
+    want = {}
+    for tid, (o_v, o_n) in enumerate((("degree", "asc"), ("random", "desc"))):
+        want[tid] = oracle_port.keyed_schur(optr, ocol, ow, t, o_v, o_n, seed=11 + tid, view=0)
+    got, errs = {}, []
+
+    def work(tid, o_v, o_n):
+        try:
+            st = torch.cuda.Stream()
+            with torch.cuda.stream(st):
+                g = rlap_b200.prepare(torch.from_numpy(ei).cuda(), None, n)
+                for rep in range(6):
+                    (r, c, w), vp = rlap_b200.schur_views(g, t, o_v, o_n, num_views=3, seed=11 + tid, dtype=None)
+                    got[(tid, rep)] = (r[:int(vp[1])].cpu().numpy(), c[:int(vp[1])].cpu().numpy(), w[:int(vp[1])].cpu().numpy())
+        except Exception as ex:   # pragma: no cover
+            errs.append(ex)
+
+    th = [threading.Thread(target=work, args=(0, "degree", "asc")), threading.Thread(target=work, args=(1, "random", "desc"))]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    assert not errs, errs
+    for (tid, rep), (r, c, w) in got.items():
+        r0, c0, w0 = want[tid]
+        assert np.array_equal(r, r0) and np.array_equal(c, c0) and np.array_equal(w.view(np.uint32), w0.view(np.uint32)), (tid, rep)
+
+
+@pytest.mark.gpu
+def test_unweighted_and_colptr_outputs_match_packed_rows():
+    """schur_views(weights=False) and (colptr=True, weights=False) are the packed rows minus what they leave out"""
+    import rlap_b200
+    name, ei, n, gptr, t = util.small_cases()[1]
+    g = _gpu_graph(ei, None, n, gptr)
+    (r, c, w), vp = rlap_b200.schur_views(g, t, "degree", "asc", num_views=3, seed=5, dtype=None)
+    (r2, c2, w2), vp2 = rlap_b200.schur_views(g, t, "degree", "asc", num_views=3, seed=5, dtype=None, weights=False)
+    assert w2 is None and torch.equal(r, r2) and torch.equal(c, c2) and torch.equal(vp, vp2)
+    (r3, cp3, w3), vp3 = rlap_b200.schur_views(g, t, "degree", "asc", num_views=3, seed=5, dtype=None, weights=False, colptr=True)
+    assert w3 is None and torch.equal(r, r3)
+    col = rlap_b200.ops.expand_cols(cp3.cpu(), vp3)
+    assert torch.equal(col, c.cpu())
+
+
+@pytest.mark.gpu
+def test_second_device_in_one_process(oracle_port):
+    """function attributes, streams and the host mailbox are per device: the same process runs the path on
+    cuda:1 after cuda:0 when the box has two GPUs"""
+    import rlap_b200
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs in one box")
+    name, ei, n, gptr, t = util.small_cases()[2]
+    optr, ocol, ow = oracle_port.ingest(ei, None, n)
+    r0, c0, w0 = oracle_port.keyed_schur(optr, ocol, ow, t, "coarsen", "asc", seed=9, view=0)
+    for d in (0, 1, 0):
+        g = rlap_b200.prepare(torch.from_numpy(ei).to(f"cuda:{d}"), None, n)
+        (r, c, w), vp = rlap_b200.schur_views(g, t, "coarsen", "asc", num_views=2, seed=9, dtype=None)
+        assert r.device.index == d
+        e = int(vp[1])
+        assert np.array_equal(r[:e].cpu().numpy(), r0) and np.array_equal(w[:e].cpu().numpy().view(np.uint32), w0.view(np.uint32))
