@@ -14,8 +14,8 @@ unmodified C++ built against a container-only Eigen stand-in) on all host cores.
 Configs (BASELINE.json `configs`):
   C1  BA n=100, m=50, num_remove=50, random/asc (the reference's README / test example), 256 views per step
   C2  Cora-shaped SBM n=2708, 10556 directed edges, num_remove=812 (30 %), any o_v/o_n (default degree/asc), 256 views
-  C3  PROTEINS-shaped batch of 1113 graphs (~39 nodes each), 2 views of every graph per step, num_remove = n_g // 2 per
-      graph; a "view" is one augmented graph (2226 per step). The reference arm follows the reference's own call
+  C3  PROTEINS-shaped batch of 1113 graphs (~39 nodes each), 16 views of every graph per step, num_remove = n_g // 2 per
+      graph; a "view" is one augmented graph (17808 per step). The reference arm follows the reference's own call
       pattern: unions of 128 graphs per call (scripts/graph_shared.py:139-146, DataLoader(batch_size=128))
   C4  arxiv-shaped BA n=169343, m=7 (~2.37 M directed edges), num_remove=50 %, degree/asc, 64 views per step (headline)
   C5  products-shaped SBM n=2449029, 123.7 M directed edges, coarsen, num_remove=50 %, 4 views per step
@@ -42,7 +42,7 @@ CONFIGS = {
                workload="C1 Barabasi-Albert graph n=100 m=50 (README/tests example), num_remove=50"),
     "C2": dict(o_v="degree", o_n="asc", views=256,
                workload="C2 Cora-shaped SBM n=2708 E=10556 directed, num_remove=812 (30%)"),
-    "C3": dict(o_v="random", o_n="asc", views=2,
+    "C3": dict(o_v="random", o_n="asc", views=16,
                workload="C3 PROTEINS-shaped batch of 1113 graphs (~39 nodes each), num_remove=50% per graph, one view = one augmented graph"),
     "C4": dict(o_v="degree", o_n="asc", views=64,
                workload="C4 arxiv-shaped BA graph n=169343 E~2.37M directed, num_remove=50%"),
@@ -440,10 +440,13 @@ def run_ours(args):
     timed_stats = stats_acc[args.warmup:]
     n_launch = launches["n"] * args.steps // (args.steps + args.warmup)
     clocks = sampler.stop()
-    ms_e2e, _ = timed(make_e2e("rows"), args.steps, max(args.warmup, 1), e2e=True)
-    host_bufs[0].clear(); host_bufs[1].clear()
-    ms_csc, _ = timed(make_e2e("csc"), args.steps, max(args.warmup, 1), e2e=True)
-    host_bufs[0].clear(); host_bufs[1].clear()
+    if args.skip_e2e:
+        ms_e2e = ms_csc = float("nan")
+    else:
+        ms_e2e, _ = timed(make_e2e("rows"), args.steps, max(args.warmup, 1), e2e=True)
+        host_bufs[0].clear(); host_bufs[1].clear()
+        ms_csc, _ = timed(make_e2e("csc"), args.steps, max(args.warmup, 1), e2e=True)
+        host_bufs[0].clear(); host_bufs[1].clear()
 
     # single-call latency of the reference's own call shape (one view through ops.approximate_cholesky, device
     # resident edge_index in, [E',3] float64 out), the figure to put beside the reference's per-call time
@@ -461,8 +464,8 @@ def run_ours(args):
     units = wl.units
     ms_step = ms_total / args.steps
     value = world * V * units * args.steps / (ms_total / 1e3)
-    e2e_value = world * V * units * args.steps / (ms_e2e / 1e3)
-    csc_value = world * V * units * args.steps / (ms_csc / 1e3)
+    e2e_value = None if args.skip_e2e else world * V * units * args.steps / (ms_e2e / 1e3)
+    csc_value = None if args.skip_e2e else world * V * units * args.steps / (ms_csc / 1e3)
 
     # roofline of the dominant kernel (k_eliminate: ordering + elimination of all views of a step),
     # algorithmic bytes per SURVEY.md §8(d): 8n (ordering) + 8D (adjacency read once) + 24F (fill edges, both
@@ -498,11 +501,11 @@ def run_ours(args):
         "edges_per_sec": value / units * E,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(ei_pinned.numel() * 8),
-                "d2h_bytes_per_step": int(d2h_bytes.get("rows", 0)), "ms_per_step": ms_e2e / args.steps, "mode": "rows",
+                "d2h_bytes_per_step": int(d2h_bytes.get("rows", 0)), "ms_per_step": None if args.skip_e2e else ms_e2e / args.steps, "mode": "rows",
                 "api": "ops.prepare + ops.schur_views from pinned host edge_index; packed (row, col, w) rows copied back to "
                        "pinned host on a copy stream, overlapping the next step (2 buffer sets)"},
         "e2e_csc_unweighted": {"value": csc_value, "unit": UNIT, "d2h_bytes_per_step": int(d2h_bytes.get("csc", 0)),
-                               "ms_per_step": ms_csc / args.steps,
+                               "ms_per_step": None if args.skip_e2e else ms_csc / args.steps,
                                "api": "the same with schur_views(colptr=True, weights=False): the host receives the unweighted "
                                       "CSC adjacency (row ids + column pointers) of every view, the form the reference's GCL "
                                       "adapters keep (they drop the weights, scripts/augmentor_benchmarks.py:88-96)"},
@@ -547,6 +550,7 @@ def main():
     ap.add_argument("--views", type=int, default=None, help="views per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true", help="auxiliary runs only: no host-buffer loop (e2e is reported as null)")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     args.o_v = args.o_v or cfg["o_v"]

@@ -39,20 +39,32 @@ class rLap:
         self.keep_weights = keep_weights
         self.seed = seed
         self.num_remove = 0
+        self._views_drawn = 0     # a seeded augmentor draws views seed/0, seed/1, ...: fresh randomness at every call,
+                                  # reproducible as a whole (the reference draws from std::random_device every time)
 
     def views(self, edge_index: Tensor, edge_weights: Optional[Tensor] = None, num_views: int = 1,
-              num_nodes: Optional[int] = None) -> List[Tuple[Tensor, Optional[Tensor]]]:
-        """num_views independent views in one batched call: [(edge_index [2,E'] int64, weights or None), ...]"""
+              num_nodes: Optional[int] = None, relabel: bool = False):
+        """num_views independent views in one batched call: [(edge_index [2,E'] int64, weights or None), ...].
+        relabel=True: the views come compacted to their surviving nodes (relabelled inside the emission kernel) and
+        every entry is (nodes, edge_index', weights or None) like `compact_relabel` returns."""
         n = _num_nodes(edge_index) if num_nodes is None else num_nodes
         self.num_remove = int(self.frac * n)
         g = ops.prepare(edge_index, edge_weights, n)
-        (row, col, w), vp = ops.schur_views(g, self.num_remove, self.o_v, self.o_n, num_views=num_views,
-                                            seed=self.seed, dtype=None)
+        base = self._views_drawn
+        self._views_drawn += num_views
+        res = ops.schur_views(g, self.num_remove, self.o_v, self.o_n, num_views=num_views, seed=self.seed,
+                              view_base=base if self.seed is not None else 0, dtype=None, weights=self.keep_weights,
+                              relabel=relabel)
+        ((row, col, w), newid), vp = (res[0] if relabel else (res[0], None)), res[1]
         out = []
         for v in range(num_views):
             s, e = int(vp[v]), int(vp[v + 1])
             ei = torch.stack([row[s:e], col[s:e]]).long().to(edge_index.device)
-            out.append((ei, w[s:e].to(edge_index.device) if self.keep_weights else None))
+            wv = w[s:e].to(edge_index.device) if self.keep_weights else None
+            if relabel:
+                out.append(((newid[v] >= 0).nonzero().reshape(-1).to(edge_index.device), ei, wv))
+            else:
+                out.append((ei, wv))
         return out
 
     def augment(self, g):
@@ -112,8 +124,7 @@ class rLapPPRDiffusion:
             self.refresh_cache_counter += 1
             return self._cache
         x, edge_index, edge_weights = g.unfold()
-        ei, w = self.rlap.views(edge_index, edge_weights, 1)[0]
-        nodes, sub_ei, sub_w = compact_relabel(ei, w)
+        nodes, sub_ei, sub_w = self.rlap.views(edge_index, edge_weights, 1, relabel=True)[0]   # compacted by the emission kernel
         if self.diffusion is not None:
             dei, dw = self.diffusion(sub_ei, sub_w)
         else:

@@ -547,16 +547,16 @@ struct LaneSlot {                 // element e of this lane: A[e * 32], K[e * 32
 // `cross` / `cross_idx`: the neighbour whose live counter this star moved to the segment's level or below (at most
 // one per star: the last one in o_n order, or the contraction target); the caller appends it to the low list with
 // one warp-collective push.
+// first half: gather the live entries into the lane's slot (loads only: the pool reservation of the chunk is in flight
+// meanwhile). Returns the entry count; *nbase_out = how many of them came from the (ascending) base row.
 template <class PT>
-__device__ bool eliminate_star_lane(const PT& P, const RoundCtx& rc, unsigned int idx, int b, int nb,
-                                    long long slot0, int nslots, int M, LaneSlot sl, int& made_out, int& len_out,
-                                    const LowAppender& la, bool& cross, unsigned int& cross_idx) {
-    const int view = (int)(idx / (unsigned)P.n), v = (int)(idx % (unsigned)P.n);
+__device__ int lane_star_gather(const PT& P, unsigned int idx, int b, int nb, LaneSlot sl, uint32_t* wmaxb_out,
+                                int* nbase_out) {
+    const int view = (int)(idx / (unsigned)P.n);
     const size_t vb = (size_t)view * (size_t)P.n;
-    const uint32_t view_id = P.view_base + (uint32_t)view;
-    int4* pool = P.pool + (size_t)view * (size_t)P.pool_cap;
-    // ---- gather the live entries: base row four at a time (ids and weights, then the dead tests together), then the
-    // fill list with the next hop in flight while the previous entry's neighbour is tested
+    const int4* pool = P.pool + (size_t)view * (size_t)P.pool_cap;
+    // base row four at a time (ids and weights, then the dead tests together), then the fill list with the next hop in
+    // flight while the previous entry's neighbour is tested
     int p = ldcg_i32(head_p(P, idx));
     int cnt = 0;
     uint32_t wmaxb = 0;
@@ -580,7 +580,7 @@ __device__ bool eliminate_star_lane(const PT& P, const RoundCtx& rc, unsigned in
             }
         }
     }
-    const int nbase = cnt;
+    *nbase_out = cnt;
     {
         int4 pe = make_int4(-1, 0, -1, 0);
         while (true) {
@@ -596,6 +596,21 @@ __device__ bool eliminate_star_lane(const PT& P, const RoundCtx& rc, unsigned in
             p = en.z;
         }
     }
+    *wmaxb_out = wmaxb;
+    return cnt;
+}
+
+// second half: order, sample, push. `cross` / `cross_idx`: the neighbour whose live counter this star moved to the
+// segment's level or below (at most one per star: the last one in o_n order, or the contraction target); the caller
+// appends it to the low list with one warp-collective push.
+template <class PT>
+__device__ bool eliminate_star_lane(const PT& P, const RoundCtx& rc, unsigned int idx, int cnt, uint32_t wmaxb, int nbase,
+                                    long long slot0, int nslots, int M, LaneSlot sl, int& made_out, int& len_out,
+                                    const LowAppender& la, bool& cross, unsigned int& cross_idx) {
+    const int view = (int)(idx / (unsigned)P.n), v = (int)(idx % (unsigned)P.n);
+    const size_t vb = (size_t)view * (size_t)P.n;
+    const uint32_t view_id = P.view_base + (uint32_t)view;
+    int4* pool = P.pool + (size_t)view * (size_t)P.pool_cap;
     if (cnt > LCAP || 2 * (cnt - 1) > nslots) return false;   // more live entries than the counter announced: not this path
     const int L = cnt;
     // ---- order by neighbour (the base entries are ascending already); a multi-edge sends the star to the cooperative path
@@ -848,45 +863,59 @@ __device__ void run_warp_items(const PT& P, const RoundCtx& rc, uint64_t* smem, 
     const bool full = P.full;
     enum { K_NONE = 0, K_LANE = 1, K_TILE = 2, K_SMEM = 3 };
     // pool slots are reserved once per chunk and tier: 2 per possible fill (L <= live), one atomic per view present in
-    // the chunk instead of one per star
-    auto reserve = [&](int nslots, int view) -> long long {
-        long long slot0 = 0;
+    // the chunk instead of one per star. Issue and use are split: the atomic's round trip overlaps the gathers.
+    struct Resv { unsigned long long b0; int first, incl; bool same; };
+    auto reserve_issue = [&](int nslots, int view) -> Resv {
+        Resv r;
+        r.b0 = 0ull; r.first = 0; r.same = true;
         int incl = nslots;  // inclusive prefix over the lanes of the chunk
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             int t = __shfl_up_sync(RLAP_FULL_MASK, incl, d);
             if (lane >= d) incl += t;
         }
+        r.incl = incl;
         const unsigned need = __ballot_sync(RLAP_FULL_MASK, nslots > 0);
         if (need) {
             const int first = __ffs(need) - 1, last = 31 - __clz(need);
             const int v0 = __shfl_sync(RLAP_FULL_MASK, view, first);
-            const bool same = __all_sync(RLAP_FULL_MASK, nslots == 0 || view == v0);
-            if (same) {
+            r.first = first;
+            r.same = __all_sync(RLAP_FULL_MASK, nslots == 0 || view == v0);
+            if (r.same) {
                 const int total = __shfl_sync(RLAP_FULL_MASK, incl, last);
-                unsigned long long b0 = 0;
-                if (lane == first) b0 = atomicAdd(P.pool_cursor + v0, (unsigned long long)total);
-                b0 = __shfl_sync(RLAP_FULL_MASK, b0, first);
-                slot0 = (long long)b0 + incl - nslots;
+                if (lane == first) r.b0 = atomicAdd(P.pool_cursor + v0, (unsigned long long)total);
             } else if (nslots > 0) {
-                slot0 = (long long)atomicAdd(P.pool_cursor + view, (unsigned long long)nslots);
+                r.b0 = atomicAdd(P.pool_cursor + view, (unsigned long long)nslots);
             }
         }
-        return slot0;
+        return r;
     };
+    auto reserve_finish = [&](const Resv& r, int nslots) -> long long {
+        if (!r.same) return (long long)r.b0;
+        const unsigned long long b0 = __shfl_sync(RLAP_FULL_MASK, r.b0, r.first);
+        return (long long)b0 + r.incl - nslots;
+    };
+    // The claim of a chunk is one returning atomic on the group's cursor; it is issued one chunk ahead (the next chunk
+    // is claimed before the current one is processed), so its round trip never sits on the warp's critical path. A
+    // claim past the end of the list is harmless: the cursor is only read inside the round.
+    auto chunk_size = [&](int left) {
+        int c = left / (2 * nw);
+        c = (c + 7) & ~7;
+        return c < 8 ? 8 : (c > 32 ? 32 : c);
+    };
+    int c0_next = 0, c_next = 0;
+    if (lane == 0) {
+        c_next = chunk_size(count);
+        c0_next = start + atomicAdd(P.ctr + rc.sslot, c_next);
+    }
     while (true) {
-        int c0 = 0, chunk_now = 0;
-        if (lane == 0) {
-            const int left = count - ldcg_i32(P.ctr + rc.sslot);
-            int c = left / (2 * nw);
-            c = (c + 7) & ~7;
-            c = c < 8 ? 8 : (c > 32 ? 32 : c);
-            c0 = start + atomicAdd(P.ctr + rc.sslot, c);
-            chunk_now = c;
-        }
-        c0 = __shfl_sync(RLAP_FULL_MASK, c0, 0);
-        chunk_now = __shfl_sync(RLAP_FULL_MASK, chunk_now, 0);
+        const int c0 = __shfl_sync(RLAP_FULL_MASK, c0_next, 0);
+        const int chunk_now = __shfl_sync(RLAP_FULL_MASK, c_next, 0);
         if (c0 >= end) break;
+        if (lane == 0) {
+            c_next = chunk_size(end - (c0 + chunk_now));
+            c0_next = start + atomicAdd(P.ctr + rc.sslot, c_next);
+        }
         const int it = c0 + lane;
         unsigned int idx = 0xffffffffu;
         int lv = -1, kind = K_NONE, b = 0, nb = 0, nfill = 0, M = -1, view = -1;
@@ -921,12 +950,15 @@ __device__ void run_warp_items(const PT& P, const RoundCtx& rc, uint64_t* smem, 
         // ---- lane stars
         if (__any_sync(RLAP_FULL_MASK, kind == K_LANE)) {
             const int nslots = (kind == K_LANE && lv >= 2) ? 2 * (lv - 1) : 0;
-            const long long slot0 = reserve(nslots, view);
+            const Resv rv = reserve_issue(nslots, view);
             bool cross = false;
             unsigned int cross_idx = 0;
-            int made = 0, len = 0;
+            int made = 0, len = 0, cnt = 0, nbase = 0;
+            uint32_t wmaxb = 0;
+            if (kind == K_LANE) cnt = lane_star_gather(P, idx, b, nb, slot, &wmaxb, &nbase);
+            const long long slot0 = reserve_finish(rv, nslots);
             if (kind == K_LANE) {
-                if (eliminate_star_lane(P, rc, idx, b, nb, slot0, nslots, M, slot, made, len, la, cross, cross_idx)) {
+                if (eliminate_star_lane(P, rc, idx, cnt, wmaxb, nbase, slot0, nslots, M, slot, made, len, la, cross, cross_idx)) {
                     kind = K_NONE;
                 } else {
                     // handed to the cooperative path, which reserves its own slots: these stay tombstones
@@ -963,7 +995,8 @@ __device__ void run_warp_items(const PT& P, const RoundCtx& rc, uint64_t* smem, 
             __syncwarp();
             int nslots = 0;
             if (kind == K_TILE && lv >= 2) nslots = full ? lv * (lv - 1) : 2 * (lv - 1);
-            const long long slot0 = reserve(nslots, view);
+            const Resv rv = reserve_issue(nslots, view);
+            const long long slot0 = reserve_finish(rv, nslots);
             const unsigned m32 = __ballot_sync(RLAP_FULL_MASK, kind == K_TILE);
             PendingPush pend;
             run_tier<32>(P, rc, m32, idx, b, nb, nfill, fbuf, slot0, nslots, M, ls, pend, la);

@@ -111,7 +111,7 @@ def prepare(edge_index: Tensor, edge_weights: Optional[Tensor], num_nodes: int,
 def schur_views(graph: Graph, num_remove, o_v: str, o_n: str, num_views: int = 1, seed: Optional[int] = None,
                 view_base: int = 0, full_clique: bool = False, shared_order: bool = False, dtype=torch.float64,
                 pool_cap: int = 0, scratch_cap: int = 0, return_stats: bool = False, colptr: bool = False,
-                check_live: bool = False, weights: bool = True):
+                check_live: bool = False, weights: bool = True, relabel: bool = False):
     """num_views independent randomized Schur-complement views of `graph`.
 
     Returns (edge_info, view_ptr): edge_info is [sum E'_v, 3] (row, col, weight) of `dtype`
@@ -121,7 +121,11 @@ def schur_views(graph: Graph, num_remove, o_v: str, o_n: str, num_views: int = 1
     colptr=True (with dtype=None): the `col` array is replaced by the per-view column pointers, an int32 tensor
     [num_views, n + 1] (rows of a view are sorted by column, so col is implied; `expand_cols` rebuilds it on the
     host) - a third less to move for consumers behind a PCIe link. weights=False (with dtype=None): no weight array
-    is written (w is None): the unweighted view the reference's GCL adapters keep."""
+    is written (w is None): the unweighted view the reference's GCL adapters keep.
+    relabel=True: survivor compaction + relabelling inside the emission (what the reference's adapters do afterwards
+    with torch.unique + subgraph(relabel_nodes=True), scripts/augmentor_benchmarks.py:149-155): the row / col ids of
+    view v are ranks among that view's vertices with at least one edge, and the call returns one more value, `newid`
+    int32 [num_views, n] (-1 for vertices without edges; `(newid[v] >= 0).nonzero()` is the sorted node list)."""
     assert o_v in _O_V
     assert o_n in _O_N
     L = _native.lib()
@@ -163,6 +167,12 @@ def schur_views(graph: Graph, num_remove, o_v: str, o_n: str, num_views: int = 1
             break
         total = int(rows.sum())
         view_ptr = torch.from_numpy(np.concatenate([[0], np.cumsum(rows)]).astype(np.int64))
+        newid, nid_ptr = None, 0
+        if relabel:
+            newid = torch.empty(V * graph.n + 1, dtype=torch.int32, device=dev)
+            _native.check(L.rlap_schur_relabel(graph.n, graph.nnz, V, ws.data_ptr(), wsb.value, newid.data_ptr(), 0, stream),
+                          "schur_relabel")
+            nid_ptr = newid.data_ptr()
         if dtype is None:
             orow = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
             ow = torch.empty(max(total, 1), dtype=torch.float32, device=dev) if weights else None
@@ -172,21 +182,23 @@ def schur_views(graph: Graph, num_remove, o_v: str, o_n: str, num_views: int = 1
                               "schur_colptr")
             else:
                 ocol = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
-            _native.check(L.rlap_schur_emit(graph.n, graph.nnz, graph.ptr.data_ptr(), graph.col.data_ptr(),
-                                            graph.w.data_ptr(), V, ws.data_ptr(), wsb.value, orow.data_ptr(),
-                                            0 if colptr else ocol.data_ptr(), ow.data_ptr() if weights else 0, 0, stream),
-                          "schur_emit")
+            _native.check(L.rlap_schur_emit_ids(graph.n, graph.nnz, graph.ptr.data_ptr(), graph.col.data_ptr(),
+                                                graph.w.data_ptr(), V, ws.data_ptr(), wsb.value, orow.data_ptr(),
+                                                0 if colptr else ocol.data_ptr(), ow.data_ptr() if weights else 0, 0,
+                                                nid_ptr, stream), "schur_emit")
             out = (orow[:total], ocp if colptr else ocol[:total], ow[:total] if weights else None)
         else:
             o64 = torch.empty((max(total, 1), 3), dtype=torch.float64, device=dev)
-            _native.check(L.rlap_schur_emit(graph.n, graph.nnz, graph.ptr.data_ptr(), graph.col.data_ptr(),
-                                            graph.w.data_ptr(), V, ws.data_ptr(), wsb.value, 0, 0, 0, o64.data_ptr(),
-                                            stream), "schur_emit")
+            _native.check(L.rlap_schur_emit_ids(graph.n, graph.nnz, graph.ptr.data_ptr(), graph.col.data_ptr(),
+                                                graph.w.data_ptr(), V, ws.data_ptr(), wsb.value, 0, 0, 0, o64.data_ptr(),
+                                                nid_ptr, stream), "schur_emit")
             out = o64[:total]
             if dtype != torch.float64:
                 out = out.to(dtype)
         # the library forgets the workspace before its memory goes back to the allocator
         L.rlap_schur_release(ws.data_ptr())
+    if relabel:
+        out = (out, newid[: V * graph.n].view(V, graph.n))
     if return_stats:
         names = ["rounds", "fills", "pool_used_max", "max_star", "raw_entries_read", "rows", "pool_cap", "elim_us",
                  "emit_count_us", "t_init_us", "t_phaseA_us", "t_phaseB_us", "t_phaseC_us", "t_elim_warp_us",

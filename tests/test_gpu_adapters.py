@@ -68,3 +68,41 @@ def test_chained_elimination_statistics_match_reference(oracle_port, o_n):
     assert np.all(np.abs(got[2] - want[2]) <= 0.03 * want[2]), (got[2], want[2])
     assert np.all(np.abs(got[0] - want[0]) <= 0.06 * want[0]), (got[0], want[0])
     assert got[2][-1] < got[2][0] and got[1][-1] < got[1][0]
+
+
+def test_relabelled_emission_matches_unique_searchsorted():
+    """f3: survivor compaction + relabelling inside the emission kernel (rlap_schur_relabel + rlap_schur_emit_ids) is
+    torch.unique(sorted) + searchsorted on the plain output (scripts/augmentor_benchmarks.py:149-155), bit for bit"""
+    import rlap_b200
+    from rlap_b200 import adapters
+    for name, ei, n, gptr, t in util.small_cases()[:4]:
+        g = rlap_b200.prepare(torch.from_numpy(ei).cuda(), None, n)
+        for o_v in ("random", "degree", "coarsen"):
+            (row, col, w), vp = rlap_b200.schur_views(g, t, o_v, "asc", num_views=3, seed=9, dtype=None)
+            ((r2, c2, w2), newid), vp2 = rlap_b200.schur_views(g, t, o_v, "asc", num_views=3, seed=9, dtype=None, relabel=True)
+            assert torch.equal(vp, vp2) and torch.equal(w, w2) and newid.shape == (3, n)
+            for v in range(3):
+                s, e = int(vp[v]), int(vp[v + 1])
+                eiv = torch.stack([row[s:e], col[s:e]]).long()
+                nodes, sub, _ = adapters.compact_relabel(eiv)
+                assert torch.equal((newid[v] >= 0).nonzero().reshape(-1), nodes), (name, o_v, v)
+                assert torch.equal(torch.stack([r2[s:e], c2[s:e]]).long(), sub), (name, o_v, v)
+
+
+def test_seeded_augmentor_draws_fresh_views_and_matches_oracle(oracle_port):
+    """a seeded rLap returns a different view at every call (it used to repeat view 0), reproducible as a
+    sequence, and each one is the oracle's view (seed, call index) - the adapter output compared with the oracle"""
+    from rlap_b200 import adapters, graphs
+    n = 2708
+    ei_np = graphs.sbm(n, 7, 5278, seed=0)
+    ei = torch.from_numpy(ei_np).cuda()
+    optr, ocol, ow = oracle_port.ingest(ei_np, None, n)
+    aug = adapters.rLap(0.3, o_v="degree", o_n="asc", seed=5, keep_weights=True)
+    outs = [aug(None, ei)[1:] for _ in range(3)]
+    for k, (e, w) in enumerate(outs):
+        r0, c0, w0 = oracle_port.keyed_schur(optr, ocol, ow, int(0.3 * n), "degree", "asc", seed=5, view=k)
+        assert np.array_equal(e[0].cpu().numpy(), r0) and np.array_equal(e[1].cpu().numpy(), c0)
+        assert np.array_equal(w.cpu().numpy().view(np.uint32), w0.view(np.uint32))
+    assert not torch.equal(outs[0][0], outs[1][0])
+    again = adapters.rLap(0.3, o_v="degree", o_n="asc", seed=5, keep_weights=True)
+    assert torch.equal(again(None, ei)[1], outs[0][0])

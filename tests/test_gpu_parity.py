@@ -366,3 +366,36 @@ def test_second_device_in_one_process(oracle_port):
         assert r.device.index == d
         e = int(vp[1])
         assert np.array_equal(r[:e].cpu().numpy(), r0) and np.array_equal(w[:e].cpu().numpy().view(np.uint32), w0.view(np.uint32))
+
+
+@pytest.mark.gpu
+def test_degree_initial_bucket_and_first_pop_match_reference(oracle_port):
+    """a7: the initial keys / buckets are the reference's (preconditioner.cc:125-165: key = stored entries of the column,
+    bucket head = highest id). With num_remove = 1 the reference pops exactly the head of the lowest non-empty bucket,
+    and so must the CUDA path (the last round keeps the highest ids of its independent set); with a larger budget the
+    first round of the keyed schedule is the independent set of that bucket, computed here from the degrees alone."""
+    import rlap_b200
+    for name, ei, n, gptr, t in util.small_cases()[:3]:
+        info = util.edge_info(ei)
+        deg = np.bincount(ei[1], minlength=n)
+        m = deg.min()
+        head = int(np.nonzero(deg == m)[0].max())
+        g = _gpu_graph(ei, None, n, None)
+        for o_v in ("degree", "coarsen"):
+            ref = oracle_port.ref_approximate_cholesky(info, n, 1, o_v, "asc")
+            gone_ref = set(range(n)) - set(ref[:, 1].astype(np.int64).tolist())
+            (row, col, w), vp = rlap_b200.schur_views(g, 1, o_v, "asc", num_views=1, seed=1, dtype=None)
+            gone_gpu = set(range(n)) - set(col.cpu().numpy().tolist())
+            iso = set(np.nonzero(deg == 0)[0].tolist())
+            assert gone_ref - iso == {head} - iso and gone_gpu - iso == gone_ref - iso, (name, o_v, head, gone_ref, gone_gpu)
+        # first round of the keyed schedule = bucket members without a higher-id bucket neighbour
+        optr, ocol, ow = oracle_port.ingest(ei, None, n)
+        order = oracle_port.keyed_schur(optr, ocol, ow, n // 2, "degree", "asc", seed=1, return_order=True)[-1]
+        bucket = deg == m
+        blocked = np.zeros(n, dtype=bool)
+        src, dst = ei[0], ei[1]
+        sel = bucket[src] & bucket[dst] & (src > dst)
+        blocked[dst[sel]] = True
+        first = np.nonzero(bucket & ~blocked)[0]
+        if first.size <= n // 2:
+            assert np.array_equal(np.nonzero(order == 0)[0], first), name
