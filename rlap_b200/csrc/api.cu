@@ -28,7 +28,9 @@ int eliminate_max_blocks();
 cudaError_t launch_emit_colptr(const SchurParams& P, int* colptr, cudaStream_t stream);
 cudaError_t launch_combine_groups(int K, const int* gctr, const unsigned long long* gstats, int* ctr,
                                   unsigned long long* stats, cudaStream_t stream);
-cudaError_t launch_emit_count(const SchurParams& P, long long* total_dev, cudaStream_t stream);
+constexpr int EMIT_AUX = 6;   // side streams of the emission's merge-path sort kernels
+cudaError_t launch_emit_count(const SchurParams& P, long long* total_dev, cudaStream_t stream, cudaStream_t* aux,
+                              cudaEvent_t* aux_ev);
 cudaError_t launch_emit_write(const SchurParams& P, int* out_row, int* out_col, float* out_w, double* out_f64,
                               const int* newid, cudaStream_t stream);
 cudaError_t launch_relabel(const SchurParams& P, int* newid, long long* base_dev, long long* view_nodes, cudaStream_t stream);
@@ -74,6 +76,8 @@ constexpr int MAX_GROUPS = 64;     // view groups of one call (the parameter tab
 struct ThreadDevice {
     Mailbox mail;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    cudaStream_t aux[EMIT_AUX] = {nullptr};          // created on first use on this device
+    cudaEvent_t aux_ev[EMIT_AUX + 1] = {nullptr};
     std::vector<int> gp;
     std::vector<SchurParams> groups;   // host copy of the parameter blocks of the view groups
     std::vector<int> block_group;
@@ -262,7 +266,7 @@ struct SchurLayout {
 // independent, and a barrier over all of them makes every phase of every view wait for the slowest chain of any view
 // (45 % of the warp time in the single-barrier profile, profiles/README.md). A group of one block has no global
 // barrier at all.
-constexpr int MAX_SCRATCH_SLOTS = 512;   // >= blocks of a launch (2 per SM)
+constexpr int MAX_SCRATCH_SLOTS = 640;   // >= blocks of a launch (4 per SM)
 static long long default_pool_cap(long long nnz) { return 2 * nnz + 4096; }
 static long long default_scratch_cap(long long n) {
     long long c = n < 65536 ? n : 65536;
@@ -478,7 +482,11 @@ int rlap_schur_eliminate(int64_t n, int64_t nnz, const int32_t* csr_ptr, const i
     }
 #endif
     CK(cudaEventRecord(ev[1], stream));
-    CK(launch_emit_count(P, L.total_dev, stream));
+    if (!td->aux[0]) {
+        for (int i = 0; i < EMIT_AUX; i++) CK(cudaStreamCreateWithFlags(&td->aux[i], cudaStreamNonBlocking));
+        for (int i = 0; i <= EMIT_AUX; i++) CK(cudaEventCreateWithFlags(&td->aux_ev[i], cudaEventDisableTiming));
+    }
+    CK(launch_emit_count(P, L.total_dev, stream, td->aux, td->aux_ev));
     CK(cudaEventRecord(ev[2], stream));
     const size_t mail_words = (size_t)CTR_COUNT + ST_COUNT + 2 * (size_t)n_views + 2;
     if (g_mail.ensure(mail_words)) return cuda_fail(cudaErrorMemoryAllocation, "cudaHostAlloc(mailbox)");
@@ -521,7 +529,7 @@ int rlap_schur_eliminate(int64_t n, int64_t nnz, const int32_t* csr_ptr, const i
     if ((flags & 128) && getenv("RLAP_DEBUG_TIMERS")) {   // mean barrier wait per warp and phase, microseconds
         int blocks = 0;
         eliminate_grid(&blocks);
-        const double nwarps = (double)blocks * WARPS_PER_BLOCK;
+        const double nwarps = (double)blocks * ELIM_WARPS;
         static const char* nm[6] = {"init", "A", "B", "C", "D1", "D2"};
         fprintf(stderr, "rlap timers (us): k_eliminate %.0f |", 0.0 + (double)(stats ? stats[7] : 0));
         for (int i = 0; i < 6; i++)

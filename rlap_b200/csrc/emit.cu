@@ -614,15 +614,35 @@ __global__ void __launch_bounds__(WR_WARPS * 32) k_emit_write(SchurParams P, int
             const int p_end = __shfl_sync(RLAP_FULL_MASK, b + nb, 31);
             int run = 0;       // alive base entries of flat survivors seen so far
             int rs = 0;        // value of `run` at the start of this lane's row
-            for (int p0 = p_begin; p0 < p_end; p0 += 32) {
+            // Software pipeline over the steps of the sweep: the ids / weights of step s + 2 and the state look-ups of
+            // step s + 1 are in flight while step s is ranked and written (the look-up needs the id: two round trips
+            // per step otherwise, exposed 14 times per batch).
+            uint32_t c2 = 0xffffffffu, c1 = 0xffffffffu;   // ids of the steps two / one ahead
+            float w2 = 0.f, w1 = 0.f;
+            int o1 = 0;
+            bool al1 = false;                             // owner and liveness of the step one ahead
+            auto load_cw = [&](int p0, uint32_t& c, float& w) {
                 const int p = p0 + lane;
-                const bool in = p < p_end;
-                uint32_t c = 0xffffffffu;
-                float w = 0.f;
-                if (in) { c = (uint32_t)__ldg(P.col + p); w = __ldg(P.w + p); }
-                const int o = owner_of(b, p);
+                c = 0xffffffffu; w = 0.f;
+                if (p < p_end) { c = (uint32_t)__ldg(P.col + p); w = __ldg(P.w + p); }
+            };
+            auto look_up = [&](int p0, uint32_t c, int& o, bool& alive) {
+                const int p = p0 + lane;
+                o = owner_of(b, p);
                 const bool oflat = __shfl_sync(RLAP_FULL_MASK, (int)flat, o) != 0;
-                const bool alive = in && oflat && P.state[vb + c] != 2;
+                alive = p < p_end && oflat && P.state[vb + c] != 2;
+            };
+            load_cw(p_begin, c1, w1);
+            load_cw(p_begin + 32, c2, w2);
+            look_up(p_begin, c1, o1, al1);
+            for (int p0 = p_begin; p0 < p_end; p0 += 32) {
+                const uint32_t c = c1;
+                const float w = w1;
+                const int o = o1;
+                const bool alive = al1;
+                c1 = c2; w1 = w2;
+                load_cw(p0 + 64, c2, w2);
+                look_up(p0 + 32, c1, o1, al1);
                 const unsigned mask = __ballot_sync(RLAP_FULL_MASK, alive);
                 // rows that start inside this step note how many alive entries came before them
                 if (b >= p0 && b < p0 + 32) rs = run + __popc(mask & ((1u << (b - p0)) - 1u));
@@ -787,7 +807,11 @@ cudaError_t eliminate_grid(int* blocks_out);
 #define DBG_SYNC(name) do {} while (0)
 #endif
 
-cudaError_t launch_emit_count(const SchurParams& P, long long* total_dev, cudaStream_t stream) {
+// aux[0..5] / aux_ev[0..6]: side streams and events of the calling thread and device (api.cu). The seven sort kernels of
+// the merge path work on disjoint lists of a few hundred to a few thousand segments each - small, latency-bound
+// launches: forked onto the side streams they overlap instead of queueing behind one another.
+cudaError_t launch_emit_count(const SchurParams& P, long long* total_dev, cudaStream_t stream, cudaStream_t* aux,
+                              cudaEvent_t* aux_ev) {
     const size_t smem = (size_t)3 * CAP_CTA * sizeof(uint64_t);
     const size_t smem_big = (size_t)2 * CAP_BIG * sizeof(uint64_t);
     {
@@ -829,13 +853,25 @@ cudaError_t launch_emit_count(const SchurParams& P, long long* total_dev, cudaSt
     int blocks = 0;
     e = eliminate_grid(&blocks);
     if (e != cudaSuccess) return e;
-    k_emit_sort_small<<<148 * 8, 256, 0, stream>>>(P);
-    k_emit_sort_mid<2><<<148 * 8, 256, 0, stream>>>(P);
-    k_emit_sort_mid<4><<<148 * 8, 256, 0, stream>>>(P);
-    k_emit_sort_mid<8><<<148 * 4, 256, 0, stream>>>(P);
-    k_emit_sort_mid<16><<<148 * 4, 256, 0, stream>>>(P);
-    k_emit_sort_block<<<blocks, BLOCK_THREADS, smem, stream>>>(P);
-    k_emit_sort_big<<<blocks / 2, BLOCK_THREADS, smem_big, stream>>>(P);
+    e = cudaEventRecord(aux_ev[6], stream);           // fork: the lists and the staged base entries are complete
+    if (e != cudaSuccess) return e;
+    for (int i = 0; i < 6; i++) {
+        e = cudaStreamWaitEvent(aux[i], aux_ev[6], 0);
+        if (e != cudaSuccess) return e;
+    }
+    k_emit_sort_small<<<148 * 4, 256, 0, stream>>>(P);
+    k_emit_sort_mid<2><<<148 * 4, 256, 0, aux[0]>>>(P);
+    k_emit_sort_mid<4><<<148 * 4, 256, 0, aux[1]>>>(P);
+    k_emit_sort_mid<8><<<148 * 2, 256, 0, aux[2]>>>(P);
+    k_emit_sort_mid<16><<<148 * 2, 256, 0, aux[3]>>>(P);
+    k_emit_sort_block<<<blocks / 2, BLOCK_THREADS, smem, aux[4]>>>(P);
+    k_emit_sort_big<<<blocks / 4, BLOCK_THREADS, smem_big, aux[5]>>>(P);
+    for (int i = 0; i < 6; i++) {                     // join
+        e = cudaEventRecord(aux_ev[i], aux[i]);
+        if (e != cudaSuccess) return e;
+        e = cudaStreamWaitEvent(stream, aux_ev[i], 0);
+        if (e != cudaSuccess) return e;
+    }
     DBG_SYNC("k_emit_sort_*");
     return launch_exclusive_scan<long long>(P.outcnt, VN, P.outoff, P.blocksum, total_dev, stream);
 }

@@ -1015,7 +1015,16 @@ __device__ void run_warp_items(const PT& P, const RoundCtx& rc, uint64_t* smem, 
     }
 }
 
-// deferred items [start, end): one block per item in shared memory; stars beyond CAP_CTA go to the
+__device__ __forceinline__ StarBuf elim_cta_buf(uint64_t* smem) {
+    StarBuf sb;
+    sb.A = smem;
+    sb.Q = smem + ELIM_CAP_CTA;
+    sb.K = smem + 2 * ELIM_CAP_CTA;
+    sb.cap = ELIM_CAP_CTA;
+    return sb;
+}
+
+// deferred items [start, end): one block per item in shared memory; stars beyond ELIM_CAP_CTA go to the
 // NSLOT blocks that own a global scratch slot
 template <class PT>
 __device__ void run_block_items(const PT& P, const RoundCtx& rc, uint64_t* smem, CtaScratch* cs, int start,
@@ -1024,7 +1033,7 @@ __device__ void run_block_items(const PT& P, const RoundCtx& rc, uint64_t* smem,
     for (int it = start + lb; it < end; it += P.gblocks) {
         unsigned int idx = __ldcg(P.dl + it);
         int view = (int)(idx / (unsigned)P.n), v = (int)(idx % (unsigned)P.n);
-        if (ldcg_i32(live_p(P, idx)) <= CAP_CTA) eliminate_star<true>(P, rc, view, v, cta_buf(smem), cs, ls, la);
+        if (ldcg_i32(live_p(P, idx)) <= ELIM_CAP_CTA) eliminate_star<true>(P, rc, view, v, elim_cta_buf(smem), cs, ls, la);
         __syncthreads();
     }
     const int nslot = min(NSLOT, P.gblocks);   // a view group may run on fewer blocks than there are slots
@@ -1032,7 +1041,7 @@ __device__ void run_block_items(const PT& P, const RoundCtx& rc, uint64_t* smem,
         int j = 0;
         for (int it = start; it < end; it++) {
             unsigned int idx = __ldcg(P.dl + it);
-            if (ldcg_i32(live_p(P, idx)) <= CAP_CTA) continue;
+            if (ldcg_i32(live_p(P, idx)) <= ELIM_CAP_CTA) continue;
             if ((j++ % nslot) != lb) continue;
             int view = (int)(idx / (unsigned)P.n), v = (int)(idx % (unsigned)P.n);
             eliminate_star<true>(P, rc, view, v, scratch_buf(P), cs, ls, la);
@@ -1069,7 +1078,7 @@ __device__ __forceinline__ void group_sync(int* bar, int nblocks) {
 // constant-bank operand; a table in global memory costs the persistent kernel 160 B more spill stores and 0.9 ms per
 // 64 arxiv-shaped views (measured, profiles/README.md).
 constexpr int TAB_GROUPS = 64;
-constexpr int TAB_BLOCKS = 512;
+constexpr int TAB_BLOCKS = 640;    // 4 blocks per SM x 148 SMs and some
 template <int OV, int ON, bool FULL>
 struct GroupTable {
     ModeParams<OV, ON, FULL> g[TAB_GROUPS];
@@ -1081,13 +1090,13 @@ struct GroupTableRaw {               // what the host fills: same layout
 };
 
 template <int OV, int ON, bool FULL>
-__global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(const __grid_constant__ GroupTable<OV, ON, FULL> tab) {
+__global__ void __launch_bounds__(ELIM_THREADS, ELIM_CTAS_PER_SM) k_eliminate(const __grid_constant__ GroupTable<OV, ON, FULL> tab) {
     const ModeParams<OV, ON, FULL>& P = tab.g[tab.bg[blockIdx.x]];
     extern __shared__ __align__(16) uint64_t smem[];
     __shared__ CtaScratch cs;
     __shared__ int s_next, s_nsel;
-    __shared__ unsigned int s_lowbuf[WARPS_PER_BLOCK][LOWBUF];
-    __shared__ LocalStats s_stats[WARPS_PER_BLOCK];
+    __shared__ unsigned int s_lowbuf[ELIM_WARPS][LOWBUF];
+    __shared__ LocalStats s_stats[ELIM_WARPS];
     const long long tid = (long long)((int)blockIdx.x - P.gblock0) * blockDim.x + threadIdx.x;   // inside the view group
     const long long nthr = (long long)P.gblocks * blockDim.x;
     int* const bar = P.ctr + CTR_BAR;
@@ -1542,7 +1551,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_eliminate(const __grid_con
                 wfill += __popc(cm);
             };
             // member buffer of the scan part: up to 32 left over + 128 new per iteration
-            unsigned int* mbuf = (unsigned int*)((int*)smem + 6 * SEG_SM + WARPS_PER_BLOCK * WBUF) + (size_t)(threadIdx.x >> 5) * MBUF;
+            unsigned int* mbuf = (unsigned int*)((int*)smem + 6 * SEG_SM + ELIM_WARPS * WBUF) + (size_t)(threadIdx.x >> 5) * MBUF;
             int mfill = 0;
             auto test_members = [&](int first, int count) {      // warp-collective: lane i tests member first + i
                 bool cand = false, keep = false;
@@ -1797,9 +1806,12 @@ __global__ void k_setup_graphs(int n, int G, const int* gptr, const long long* n
 // dynamic shared memory of k_eliminate: the block-level star buffer (3 x CAP_CTA words) or the per-warp regions of the
 // elimination phase, whichever is larger
 static size_t eliminate_smem_bytes(bool need_keys) {
-    const size_t cta = (size_t)3 * CAP_CTA * sizeof(uint64_t);
-    const size_t warps = (size_t)WARPS_PER_BLOCK * (size_t)warp_region_words(need_keys) * sizeof(uint64_t);
-    return cta > warps ? cta : warps;
+    const size_t cta = (size_t)3 * ELIM_CAP_CTA * sizeof(uint64_t);
+    const size_t warps = (size_t)ELIM_WARPS * (size_t)warp_region_words(need_keys) * sizeof(uint64_t);
+    // phases A2 / B: six per-segment arrays of 1 024 ints + the candidate and member buffers of every warp (224 + 160 ints)
+    const size_t phases = ((size_t)6 * 1024 + (size_t)ELIM_WARPS * (224 + 160)) * sizeof(int);
+    size_t m = cta > warps ? cta : warps;
+    return m > phases ? m : phases;
 }
 
 cudaError_t launch_setup_graphs(int n, int G, const int* gptr, const long long* num_remove, int* gid, int* teff,
@@ -1855,7 +1867,7 @@ cudaError_t eliminate_grid(int* blocks_out) {
             e = cudaFuncSetAttribute(mode_kernel(m), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
             int occ = 0;
-            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mode_kernel(m), BLOCK_THREADS, smem);
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mode_kernel(m), ELIM_THREADS, smem);
             if (e != cudaSuccess) return e;
             occ_min = occ < occ_min ? occ : occ_min;
         }
@@ -1878,7 +1890,7 @@ cudaError_t launch_eliminate(const SchurParams* groups_host, int K, const int* b
     for (int b = 0; b < blocks; b++) tab.bg[b] = (unsigned short)block_group_host[b];
     void* args[] = {(void*)&tab};
     const int m = mode_index(o_v, o_n, (flags & 1) != 0);
-    return cudaLaunchCooperativeKernel(mode_kernel(m), dim3(blocks), dim3(BLOCK_THREADS), args,
+    return cudaLaunchCooperativeKernel(mode_kernel(m), dim3(blocks), dim3(ELIM_THREADS), args,
                                        eliminate_smem_bytes(mode_needs_keys(m)), stream);
 }
 

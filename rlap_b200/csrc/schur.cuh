@@ -13,6 +13,15 @@ constexpr int WARPS_PER_BLOCK = BLOCK_THREADS / 32;
 constexpr int CAP_WARP = 128;
 constexpr int CAP_CTA = CAP_WARP * WARPS_PER_BLOCK;  // 2048
 constexpr int SEL_BLOCK = 1024;                       // ids per block of the truncation search
+// the elimination kernel runs smaller blocks than the streaming kernels: four 256-thread blocks per SM, i.e. the blocks
+// of four different view groups, so that a group waiting at its barrier leaves the SM to three others
+#ifndef RLAP_ELIM_THREADS
+#define RLAP_ELIM_THREADS 256
+#endif
+constexpr int ELIM_THREADS = RLAP_ELIM_THREADS;
+constexpr int ELIM_WARPS = ELIM_THREADS / 32;
+constexpr int ELIM_CTAS_PER_SM = 1024 / ELIM_THREADS;
+constexpr int ELIM_CAP_CTA = CAP_WARP * ELIM_WARPS;   // largest star one block of the elimination kernel holds in shared memory
 
 constexpr int NSLOT = 8;                              // blocks that own a global scratch slot
 

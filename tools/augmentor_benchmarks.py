@@ -44,6 +44,41 @@ def ba_batch(n_graphs, mean_nodes, m, seed=0):
     return parts, np.asarray(ptr, dtype=np.int64)
 
 
+def build_batches(task, dataset, device=None):
+    """[(x, edge_index)] as the reference's loops see them: one whole graph (node task) or unions of 128 graphs"""
+    mk = (lambda a: torch.from_numpy(a).to(device)) if device is not None else (lambda a: torch.from_numpy(a))
+    if task == "node":
+        n, e_und, blocks = NODE_SHAPES[dataset]
+        ei = mk(graphs.sbm(n, blocks, e_und, seed=0))
+        return [(torch.zeros((n, 1), device=ei.device), ei)]
+    ng, mean_nodes, m = GRAPH_SHAPES[dataset]
+    parts, ptr = ba_batch(ng, mean_nodes, m)
+    batches = []
+    for b0 in range(0, ng, 128):       # DataLoader(dataset, batch_size=128): a batch is one union graph
+        b1 = min(b0 + 128, ng)
+        ei = mk(np.concatenate(parts[b0:b1], axis=1) - ptr[b0])
+        batches.append((torch.zeros((int(ptr[b1] - ptr[b0]), 1), device=ei.device), ei))
+    return batches
+
+
+def time_augmentor(aug, batches, repeat, sync=None):
+    """the reference's timing loop (scripts/augmentor_benchmarks.py:366-393): seconds per pass over the batches"""
+    sync = sync or (lambda: None)
+    aug(*batches[0], None)                  # build / load the extension, warm the allocator
+    sync()
+    out_t = []
+    for _ in range(repeat):
+        duration = 0.0
+        for x, ei in batches:
+            sync()
+            start = time.time()
+            aug(x, ei, None)
+            sync()
+            duration += time.time() - start
+        out_t.append(duration)
+    return out_t
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("task", choices=["node", "graph"])
@@ -60,34 +95,12 @@ def main():
     dev = torch.device("cuda")
     fraction = 0.5
     aug = adapters.rLap(fraction, o_v=args.o_v, o_n=args.o_n)
-    if args.task == "node":
-        n, e_und, blocks = NODE_SHAPES[args.dataset]
-        ei = torch.from_numpy(graphs.sbm(n, blocks, e_und, seed=0)).to(dev)
-        x = torch.zeros((n, 1), device=dev)
-        batches = [(x, ei)]
-    else:
-        ng, mean_nodes, m = GRAPH_SHAPES[args.dataset]
-        parts, ptr = ba_batch(ng, mean_nodes, m)
-        batches = []
-        for b0 in range(0, ng, 128):       # DataLoader(dataset, batch_size=128): a batch is one union graph
-            b1 = min(b0 + 128, ng)
-            ei = np.concatenate(parts[b0:b1], axis=1) - ptr[b0]
-            batches.append((torch.zeros((int(ptr[b1] - ptr[b0]), 1), device=dev), torch.from_numpy(ei).to(dev)))
-    aug(*batches[0], None)                  # build / load the extension, warm the allocator
-    torch.cuda.synchronize()
-    for _ in range(args.repeat):
-        torch.cuda.reset_peak_memory_stats()
-        duration = 0.0
-        for x, ei in batches:
-            torch.cuda.synchronize()
-            start = time.time()
-            out = aug(x, ei, None)
-            torch.cuda.synchronize()
-            duration += time.time() - start
+    batches = build_batches(args.task, args.dataset, dev)
+    torch.cuda.reset_peak_memory_stats()
+    for duration in time_augmentor(aug, batches, args.repeat, torch.cuda.synchronize):
         print("\nDURATION: {} sec\n".format(duration))
         print("PEAK DEVICE MEMORY: {:.1f} MiB".format(torch.cuda.max_memory_allocated() / 2 ** 20))
-    rows = int(out[1].shape[1])
-    print(f"last batch: {int(batches[-1][1].shape[1])} directed edges in, {rows} out, num_remove={aug.num_remove}")
+    print(f"last batch: {int(batches[-1][1].shape[1])} directed edges in, num_remove={aug.num_remove}")
 
 
 if __name__ == "__main__":

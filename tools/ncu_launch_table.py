@@ -1,11 +1,17 @@
-"""per-kernel table from an `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --csv` launch list"""
+"""per-kernel table from an `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --csv` launch list
+
+    python tools/ncu_launch_table.py launches.csv [first_id last_id]      # only the launches with first_id <= ID <= last_id
+"""
 import csv, collections, sys
 rows = list(csv.reader(open(sys.argv[1])))
+lo_id = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+hi_id = int(sys.argv[3]) if len(sys.argv) > 3 else 1 << 60
 hi = [i for i, r in enumerate(rows) if 'Kernel Name' in r][0]
 h = rows[hi]; ik = h.index('Kernel Name'); im = h.index('Metric Name'); iv = h.index('Metric Value'); iid = h.index('ID')
 d = collections.defaultdict(dict)
 for r in rows[hi + 1:]:
     if len(r) <= iv: continue
+    if not (lo_id <= int(r[iid]) <= hi_id): continue
     d[(int(r[iid]), r[ik])][r[im]] = float(r[iv].replace(',', ''))
 agg = collections.defaultdict(lambda: [0, 0.0, 0.0, 0.0])
 for (i, k), m in d.items():
