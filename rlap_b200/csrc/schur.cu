@@ -20,6 +20,12 @@
 #include "scan.cuh"
 #include "star.cuh"
 
+// keys past the bucket key that a rescan lists as well (see phase B2). Measured on the arxiv shape, 64 views: 0 -> 5.15 ms,
+// 1 -> 5.26 ms, 2 -> 5.61 ms for k_eliminate: the longer low lists cost more than the rescans they save.
+#ifndef RLAP_LVL_AHEAD
+#define RLAP_LVL_AHEAD 0
+#endif
+
 namespace rlap {
 
 __device__ __forceinline__ int graph_of(const SchurParams& P, int v) { return P.gid ? __ldg(P.gid + v) : 0; }
@@ -1281,6 +1287,7 @@ __global__ void __launch_bounds__(ELIM_THREADS, ELIM_CTAS_PER_SM) k_eliminate(co
         // live counter was seen crossing from above lvl to lvl or below by the elimination phase). While the low
         // list of a segment has an entry in play the bucket is taken from the list alone.
         constexpr int SEG_SM = 1024, WBUF = 224, MBUF = 160;
+        constexpr int LVL_AHEAD = RLAP_LVL_AHEAD;
         const int INF = 0x7fffffff;
         // (round, key) snapshots written by phase A, read by the bucket test of phase B; the emission's row offsets
         // are not needed before the elimination is over
@@ -1597,9 +1604,12 @@ __global__ void __launch_bounds__(ELIM_THREADS, ELIM_CTAS_PER_SM) k_eliminate(co
                 la.push(keep, idx);
             }
             dlap(1);
-            // B2: full scan of the segments that rescan; the level moves to the bucket key found
+            // B2: full scan of the segments that rescan. The level moves LVL_AHEAD keys past the bucket key found and
+            // the scan lists the vertices between the bucket and the level as well (they are "in play" from the next
+            // round on): the segment rescans again only when all those keys have drained, i.e. 1 + LVL_AHEAD times less
+            // often; the bucket of a round is still the minimum key alone (DESIGN.md §3.4 unchanged). LVL_AHEAD = 0 by default.
             for (long long q = tid; q < VG; q += nthr) {
-                if (ldcg_i32(mkl + q) == INF) { const int m2 = ldcg_i32(mks + q); if (m2 != INF) P.lvl[q] = m2; }
+                if (ldcg_i32(mkl + q) == INF) { const int m2 = ldcg_i32(mks + q); if (m2 != INF) P.lvl[q] = m2 + LVL_AHEAD; }
             }
             {
                 const unsigned total = nselB * un;
@@ -1640,10 +1650,13 @@ __global__ void __launch_bounds__(ELIM_THREADS, ELIM_CTAS_PER_SM) k_eliminate(co
                     for (int q4 = 0; q4 < 4; q4++) {
                         const unsigned idx = (unsigned)vw4[q4] * un + (unsigned)vx4[q4];
                         const int m = mk4[q4];
-                        const bool member = m >= 0 && st4[q4] != 2 && ((st4[q4] == 4) ? 0 : max(lv4[q4], 1)) == m;
+                        const int key = (st4[q4] == 4) ? 0 : max(lv4[q4], 1);
+                        const bool alive = m >= 0 && st4[q4] != 2;
+                        const bool member = alive && key == m;
                         const unsigned mm = __ballot_sync(RLAP_FULL_MASK, member);
                         if (member) mbuf[mfill + __popc(mm & lt)] = idx;
                         mfill += __popc(mm);
+                        la.push(alive && key > m && key <= m + LVL_AHEAD, idx);
                     }
                     __syncwarp();
                     while (mfill >= 32) { mfill -= 32; test_members(mfill, 32); }
