@@ -17,7 +17,8 @@ Configs (BASELINE.json `configs`):
   C3  PROTEINS-shaped batch of 1113 graphs (~39 nodes each), 16 views of every graph per step, num_remove = n_g // 2 per
       graph; a "view" is one augmented graph (17808 per step). The reference arm follows the reference's own call
       pattern: unions of 128 graphs per call (scripts/graph_shared.py:139-146, DataLoader(batch_size=128))
-  C4  arxiv-shaped BA n=169343, m=7 (~2.37 M directed edges), num_remove=50 %, degree/asc, 64 views per step (headline)
+  C4  arxiv-shaped BA n=169343, m=7 (~2.37 M directed edges), num_remove=50 %, degree/asc, 128 views per step (headline;
+      round 1 ran 64 per step: `--views 64` reproduces that line)
   C5  products-shaped SBM n=2449029, 123.7 M directed edges, coarsen, num_remove=50 %, 4 views per step
 """
 import argparse
@@ -44,7 +45,7 @@ CONFIGS = {
                workload="C2 Cora-shaped SBM n=2708 E=10556 directed, num_remove=812 (30%)"),
     "C3": dict(o_v="random", o_n="asc", views=16,
                workload="C3 PROTEINS-shaped batch of 1113 graphs (~39 nodes each), num_remove=50% per graph, one view = one augmented graph"),
-    "C4": dict(o_v="degree", o_n="asc", views=64,
+    "C4": dict(o_v="degree", o_n="asc", views=128,
                workload="C4 arxiv-shaped BA graph n=169343 E~2.37M directed, num_remove=50%"),
     "C5": dict(o_v="coarsen", o_n="asc", views=4,
                workload="C5 products-shaped SBM n=2449029 E~123.7M directed, num_remove=50%"),
