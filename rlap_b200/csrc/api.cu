@@ -266,7 +266,7 @@ struct SchurLayout {
 // independent, and a barrier over all of them makes every phase of every view wait for the slowest chain of any view
 // (45 % of the warp time in the single-barrier profile, profiles/README.md). A group of one block has no global
 // barrier at all.
-constexpr int MAX_SCRATCH_SLOTS = 640;   // >= blocks of a launch (4 per SM)
+constexpr int MAX_SCRATCH_SLOTS = 1280;  // >= blocks of a launch
 static long long default_pool_cap(long long nnz) { return 2 * nnz + 4096; }
 static long long default_scratch_cap(long long n) {
     long long c = n < 65536 ? n : 65536;
@@ -300,6 +300,8 @@ static SchurLayout schur_layout(long long n, long long nnz, long long G, long lo
     L.nrem_dev = c.take<long long>((size_t)G);
     L.teff_dev = c.take<int>((size_t)G);
     L.gid_dev = c.take<int>(G > 1 ? (size_t)n : 1);
+    P.nw32 = (int)((n + 31) / 32);
+    P.deadbits = c.take<unsigned int>((size_t)V * (size_t)P.nw32);
     P.state = c.take<uint8_t>(VN);
     P.lh = c.take<int>(2 * VN);
     P.rank = c.take<int>(VN);
@@ -453,6 +455,7 @@ int rlap_schur_eliminate(int64_t n, int64_t nnz, const int32_t* csr_ptr, const i
             const size_t o = (size_t)v0 * (size_t)n, og = (size_t)v0 * (size_t)G;
             Q.V = (int)Vg;
             Q.view_base = P.view_base + (uint32_t)v0;
+            Q.deadbits += (size_t)v0 * (size_t)P.nw32;
             Q.state += o; Q.lh += 2 * o; Q.rank += o; Q.blk += o; Q.candround += o;
             Q.outoff += o;                                         // phase A's (round, key) snapshots live here
             Q.pool += (size_t)v0 * (size_t)P.pool_cap;

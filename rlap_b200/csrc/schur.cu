@@ -76,7 +76,7 @@ __device__ int star_gather(const PT& P, int view, int v, StarBuf sb, CtaScratch*
         float w = 0.f;
         if (ok) {
             u = __ldg(P.col + p);
-            ok = ldcg_i32(live_p(P, vb + u)) >= 0;   // an eliminated vertex carries RLAP_LIVE_DEAD
+            ok = !is_dead(P, view, (unsigned)u);
         }
         if (ok) w = __ldg(P.w + p);
         unsigned m = __ballot_sync(RLAP_FULL_MASK, ok);
@@ -107,7 +107,7 @@ __device__ int star_gather(const PT& P, int view, int v, StarBuf sb, CtaScratch*
                 if (lane == k) { mine = en; have = true; }
                 p = en.z;
             }
-            bool ok = have && (ldcg_i32(live_p(P, vb + mine.x)) >= 0);
+            bool ok = have && !is_dead(P, view, (unsigned)mine.x);
             unsigned m = __ballot_sync(RLAP_FULL_MASK, ok);
             int base;
             if (CTA) {
@@ -363,7 +363,7 @@ __device__ void eliminate_star(const PT& P, const RoundCtx& rc, int view, int v,
             ls->raw += (unsigned long long)lraw;
         }
     }
-    if (r == 0) { P.state[vb + v] = 2; *live_p(P, vb + v) = RLAP_LIVE_DEAD; }
+    if (r == 0) { P.state[vb + v] = 2; *live_p(P, vb + v) = RLAP_LIVE_DEAD; mark_dead(P, view, (unsigned)v); }
     g_sync<CTA>();
 }
 
@@ -393,7 +393,7 @@ __device__ void eliminate_star_tile(const PT& P, const RoundCtx& rc, unsigned in
     bool dead = false;
     // dead test on the neighbour's (live, head) record: the sector is the one its live counter and list head are
     // updated in further down
-    if (a != RLAP_PAD_A) dead = ldcg_i32(live_p(P, vb + a_nbr(a))) < 0;
+    if (a != RLAP_PAD_A) dead = is_dead(P, view, a_nbr(a));
     // the previous star's pool entries: their `next` fields have arrived by now
     pend.flush(la);
     if (dead) a = RLAP_PAD_A;
@@ -524,6 +524,7 @@ __device__ void eliminate_star_tile(const PT& P, const RoundCtx& rc, unsigned in
         ls->raw += (unsigned long long)lraw;
         P.state[vb + v] = 2;
         *live_p(P, vb + v) = RLAP_LIVE_DEAD;
+        mark_dead(P, view, (unsigned)v);
     }
     __syncwarp();
 }
@@ -576,7 +577,7 @@ __device__ int lane_star_gather(const PT& P, unsigned int idx, int b, int nb, La
             w4[k] = in ? __ldg(P.w + b + p0 + k) : 0.f;
         }
 #pragma unroll
-        for (int k = 0; k < 4; k++) l4[k] = (u4[k] >= 0) ? ldcg_i32(live_p(P, vb + u4[k])) : -1;
+        for (int k = 0; k < 4; k++) l4[k] = (u4[k] >= 0) ? (is_dead(P, view, (unsigned)u4[k]) ? -1 : 0) : -1;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             if (l4[k] >= 0) {
@@ -592,7 +593,7 @@ __device__ int lane_star_gather(const PT& P, unsigned int idx, int b, int nb, La
         while (true) {
             int4 en = make_int4(-1, 0, -1, 0);
             if (p >= 0) en = __ldcg(pool + p);
-            if (pe.x >= 0 && ldcg_i32(live_p(P, vb + pe.x)) >= 0) {
+            if (pe.x >= 0 && !is_dead(P, view, (unsigned)pe.x)) {
                 if (cnt < LCAP) sl.a(cnt) = pack_a((uint32_t)pe.x, __int_as_float(pe.y));
                 cnt++;
                 wmaxb = max(wmaxb, (uint32_t)pe.y);
@@ -786,6 +787,7 @@ __device__ bool eliminate_star_lane(const PT& P, const RoundCtx& rc, unsigned in
     len_out = L;
     P.state[vb + v] = 2;
     *live_p(P, vb + v) = RLAP_LIVE_DEAD;
+    mark_dead(P, view, (unsigned)v);
     return true;
 }
 
@@ -1084,7 +1086,7 @@ __device__ __forceinline__ void group_sync(int* bar, int nblocks) {
 // constant-bank operand; a table in global memory costs the persistent kernel 160 B more spill stores and 0.9 ms per
 // 64 arxiv-shaped views (measured, profiles/README.md).
 constexpr int TAB_GROUPS = 64;
-constexpr int TAB_BLOCKS = 640;    // 4 blocks per SM x 148 SMs and some
+constexpr int TAB_BLOCKS = 1280;   // 4 blocks per SM x 148 SMs and room for other block sizes
 template <int OV, int ON, bool FULL>
 struct GroupTable {
     ModeParams<OV, ON, FULL> g[TAB_GROUPS];
@@ -1144,6 +1146,7 @@ __global__ void __launch_bounds__(ELIM_THREADS, ELIM_CTAS_PER_SM) k_eliminate(co
         }
     }
     for (long long s = tid; s < P.V; s += nthr) P.pool_cursor[s] = 0ull;
+    for (long long s = tid; s < (long long)P.V * P.nw32; s += nthr) P.deadbits[s] = 0u;
     group_sync(bar, gblocks);
 
     // phase timing (block 0, thread 0; nanoseconds between grid barriers, waits included)

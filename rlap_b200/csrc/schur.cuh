@@ -20,7 +20,10 @@ constexpr int SEL_BLOCK = 1024;                       // ids per block of the tr
 #endif
 constexpr int ELIM_THREADS = RLAP_ELIM_THREADS;
 constexpr int ELIM_WARPS = ELIM_THREADS / 32;
-constexpr int ELIM_CTAS_PER_SM = 1024 / ELIM_THREADS;
+#ifndef RLAP_ELIM_CTAS
+#define RLAP_ELIM_CTAS (1024 / RLAP_ELIM_THREADS)
+#endif
+constexpr int ELIM_CTAS_PER_SM = RLAP_ELIM_CTAS;
 constexpr int ELIM_CAP_CTA = CAP_WARP * ELIM_WARPS;   // largest star one block of the elimination kernel holds in shared memory
 
 constexpr int NSLOT = 8;                              // blocks that own a global scratch slot
@@ -109,6 +112,8 @@ struct SchurParams {
     unsigned int* dl;
     unsigned int* low;  // [2][low_cap] degree / coarsen: vertices whose key may be <= lvl (ping-pong by round parity)
     long long low_cap;
+    unsigned int* deadbits;   // [V][nw32] one bit per vertex: eliminated. The dead test of a neighbour reads this instead of
+    int nw32;                 // its 8-byte (live, head) record: 21 KB per arxiv view, resident in L2 whatever else streams
     int* ctr;          // [CTR_COUNT]
     unsigned long long* stats;  // [ST_COUNT]
     // the blocks [gblock0, gblock0 + gblocks) of the launch work on this parameter block (a view group)
@@ -136,5 +141,14 @@ struct PerDeviceOnce {
 };
 __host__ __device__ __forceinline__ int* live_p(const SchurParams& P, size_t i) { return P.lh + 2 * i; }
 __host__ __device__ __forceinline__ int* head_p(const SchurParams& P, size_t i) { return P.lh + 2 * i + 1; }
+#ifdef __CUDACC__
+// neighbour u of `view` eliminated?
+__device__ __forceinline__ bool is_dead(const SchurParams& P, int view, unsigned u) {
+    return (__ldcg(P.deadbits + (size_t)view * (size_t)P.nw32 + (u >> 5)) >> (u & 31u)) & 1u;
+}
+__device__ __forceinline__ void mark_dead(const SchurParams& P, int view, unsigned v) {
+    atomicOr(P.deadbits + (size_t)view * (size_t)P.nw32 + (v >> 5), 1u << (v & 31u));
+}
+#endif
 
 }  // namespace rlap
