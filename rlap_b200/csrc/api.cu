@@ -20,7 +20,7 @@
 namespace rlap {
 cudaError_t launch_setup_graphs(int n, int G, const int* gptr, const long long* num_remove, int* gid, int* teff,
                                 cudaStream_t stream);
-cudaError_t eliminate_grid(int* blocks_out);
+cudaError_t eliminate_grid(int* blocks_out, int o_v, int o_n, int flags);
 cudaError_t launch_eliminate(const SchurParams* groups_host, int K, const int* block_group_host, int blocks, int o_v,
                              int o_n, int flags, cudaStream_t stream);
 int eliminate_max_groups();
@@ -420,7 +420,7 @@ int rlap_schur_eliminate(int64_t n, int64_t nnz, const int32_t* csr_ptr, const i
     {
         // view groups: K groups share the blocks of one cooperative launch
         int blocks = 0;
-        CK(eliminate_grid(&blocks));
+        CK(eliminate_grid(&blocks, o_v, o_n, flags));
         if (blocks > eliminate_max_blocks()) blocks = eliminate_max_blocks();
         if (blocks > MAX_SCRATCH_SLOTS) blocks = MAX_SCRATCH_SLOTS;
         {
@@ -531,7 +531,7 @@ int rlap_schur_eliminate(int64_t n, int64_t nnz, const int32_t* csr_ptr, const i
 #ifdef RLAP_DEBUG
     if ((flags & 128) && getenv("RLAP_DEBUG_TIMERS")) {   // mean barrier wait per warp and phase, microseconds
         int blocks = 0;
-        eliminate_grid(&blocks);
+        eliminate_grid(&blocks, o_v, o_n, flags);
         const double nwarps = (double)blocks * ELIM_WARPS;
         static const char* nm[6] = {"init", "A", "B", "C", "D1", "D2"};
         fprintf(stderr, "rlap timers (us): k_eliminate %.0f |", 0.0 + (double)(stats ? stats[7] : 0));

@@ -775,7 +775,6 @@ __global__ void k_emit_colptr(SchurParams P, int* colptr) {
 // ---------------------------------------------------------------------------------------------
 // host-side launchers
 // ---------------------------------------------------------------------------------------------
-cudaError_t eliminate_grid(int* blocks_out);
 
 // -DRLAP_DEBUG with RLAP_DEBUG_SYNC=1: synchronise after every emission kernel and name the one that failed
 #ifdef RLAP_DEBUG
@@ -831,9 +830,12 @@ cudaError_t launch_emit_count(const SchurParams& P, long long* total_dev, cudaSt
         k_emit_base<<<148 * 8, 256, 0, stream>>>(P);   // list driven: a warp per merge-path vertex
         DBG_SYNC("k_emit_base");
     }
-    int blocks = 0;
-    e = eliminate_grid(&blocks);
-    if (e != cudaSuccess) return e;
+    int blocks = 296;   // two 512-thread blocks per SM
+    {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) blocks = 2 * sms;
+    }
     e = cudaEventRecord(aux_ev[6], stream);           // fork: the lists and the staged base entries are complete
     if (e != cudaSuccess) return e;
     for (int i = 0; i < 6; i++) {

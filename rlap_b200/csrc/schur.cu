@@ -1097,8 +1097,17 @@ struct GroupTableRaw {               // what the host fills: same layout
     unsigned short bg[TAB_BLOCKS];
 };
 
+// Blocks per SM, per mode. The modes that keep 32-bit shuffle keys beside the lane slots (o_n = random, coarsen) need
+// 48 KB of dynamic shared memory per block: four such blocks push the SM to its largest shared-memory carve-out, which
+// leaves 23 KB of L1 for the kernel's global loads and register spills - ncu: three times the short-scoreboard stalls
+// (shared-memory accesses queueing behind L1 misses), 5.74 ms against 3.91 ms per 64 arxiv views with room for a 56 KB
+// L1 (profiles/README.md). Three blocks per SM (24 warps, 80 registers: half the spills) is the fast side for them.
+__host__ __device__ constexpr int mode_ctas(int ov, int on, bool full) {
+    return (ELIM_THREADS == 256 && !full && (ov == 2 || on == 2)) ? 3 : ELIM_CTAS_PER_SM;
+}
+
 template <int OV, int ON, bool FULL>
-__global__ void __launch_bounds__(ELIM_THREADS, ELIM_CTAS_PER_SM) k_eliminate(const __grid_constant__ GroupTable<OV, ON, FULL> tab) {
+__global__ void __launch_bounds__(ELIM_THREADS, mode_ctas(OV, ON, FULL)) k_eliminate(const __grid_constant__ GroupTable<OV, ON, FULL> tab) {
     const ModeParams<OV, ON, FULL>& P = tab.g[tab.bg[blockIdx.x]];
     extern __shared__ __align__(16) uint64_t smem[];
     __shared__ CtaScratch cs;
@@ -1862,13 +1871,23 @@ static const void* mode_kernel(int m) {
     }
 }
 
+static int mode_ctas_of(int m) {
+    switch (m) {
+        case 2: return mode_ctas(0, 2, false);
+        case 5: return mode_ctas(1, 2, false);
+        case 6: return mode_ctas(2, 2, false);
+        default: return mode_ctas(1, 0, false);
+    }
+}
+
 // Function attributes and occupancy are per device: one cached record per device ordinal, filled under a lock.
 constexpr int MAX_DEVICES = 64;
-struct DeviceInfo { bool ready = false; int blocks = 0; };
+struct DeviceInfo { bool ready = false; int blocks[N_MODES] = {0}; int sms = 0; };
 static DeviceInfo g_dev[MAX_DEVICES];
 static std::mutex g_dev_mutex;
 
-cudaError_t eliminate_grid(int* blocks_out) {
+// largest cooperative grid of the mode's kernel on the current device
+cudaError_t eliminate_grid(int* blocks_out, int o_v, int o_n, int flags) {
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
@@ -1876,8 +1895,7 @@ cudaError_t eliminate_grid(int* blocks_out) {
     std::lock_guard<std::mutex> lk(g_dev_mutex);
     DeviceInfo& d = g_dev[dev];
     if (!d.ready) {
-        int sms = 0, occ_min = 1 << 30;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev);
         for (int m = 0; m < N_MODES; m++) {
             const size_t smem = eliminate_smem_bytes(mode_needs_keys(m));
             e = cudaFuncSetAttribute(mode_kernel(m), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1885,13 +1903,13 @@ cudaError_t eliminate_grid(int* blocks_out) {
             int occ = 0;
             e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mode_kernel(m), ELIM_THREADS, smem);
             if (e != cudaSuccess) return e;
-            occ_min = occ < occ_min ? occ : occ_min;
+            if (occ > mode_ctas_of(m)) occ = mode_ctas_of(m);
+            if (occ < 1) return cudaErrorLaunchOutOfResources;
+            d.blocks[m] = d.sms * occ;
         }
-        if (occ_min < 1) return cudaErrorLaunchOutOfResources;
-        d.blocks = sms * occ_min;   // one grid size for every mode: the view groups of a call partition it
         d.ready = true;
     }
-    *blocks_out = d.blocks;
+    *blocks_out = d.blocks[mode_index(o_v, o_n, (flags & 1) != 0)];
     return cudaSuccess;
 }
 
