@@ -21,8 +21,8 @@ namespace rlap {
 cudaError_t launch_setup_graphs(int n, int G, const int* gptr, const long long* num_remove, int* gid, int* teff,
                                 cudaStream_t stream);
 cudaError_t eliminate_grid(int* blocks_out, int o_v, int o_n, int flags);
-cudaError_t launch_eliminate(const SchurParams* groups_host, int K, const int* block_group_host, int blocks, int o_v,
-                             int o_n, int flags, cudaStream_t stream);
+cudaError_t launch_eliminate(const SchurParams* groups_host, int K, int blocks, int o_v, int o_n, int flags,
+                             cudaStream_t stream);
 int eliminate_max_groups();
 int eliminate_max_blocks();
 cudaError_t launch_emit_colptr(const SchurParams& P, int* colptr, cudaStream_t stream);
@@ -80,7 +80,6 @@ struct ThreadDevice {
     cudaEvent_t aux_ev[EMIT_AUX + 1] = {nullptr};
     std::vector<int> gp;
     std::vector<SchurParams> groups;   // host copy of the parameter blocks of the view groups
-    std::vector<int> block_group;
 };
 static ThreadDevice* thread_device() {
     static thread_local std::unordered_map<int, ThreadDevice*> per_dev;
@@ -257,8 +256,6 @@ struct SchurLayout {
     int* gctr;                 // [MAX_GROUPS][CTR_COUNT] control blocks of the view groups
     unsigned long long* gstats; // [MAX_GROUPS][ST_COUNT]
     uint64_t* gscratch;        // one scratch slot per block that may own one (NSLOT per group at most)
-    SchurParams* gparams;      // [MAX_GROUPS] device copies of the groups' parameter blocks
-    int* block_group;          // [MAX_GROUPS] group of every block of the launch
 };
 
 // The views of one call are eliminated by ONE cooperative launch of k_eliminate whose blocks are partitioned into view
@@ -292,8 +289,6 @@ static SchurLayout schur_layout(long long n, long long nnz, long long G, long lo
     P.stats = c.take<unsigned long long>(ST_COUNT);
     L.gctr = c.take<int>((size_t)MAX_GROUPS * CTR_COUNT);
     L.gstats = c.take<unsigned long long>((size_t)MAX_GROUPS * ST_COUNT);
-    L.gparams = c.take<SchurParams>((size_t)MAX_GROUPS);
-    L.block_group = c.take<int>((size_t)MAX_GROUPS);
     L.total_dev = c.take<long long>(1);
     L.viewptr_dev = c.take<long long>((size_t)V + 1);
     L.gptr_dev = c.take<int>((size_t)G + 1);
@@ -442,9 +437,7 @@ int rlap_schur_eliminate(int64_t n, int64_t nnz, const int32_t* csr_ptr, const i
         if (K > blocks) K = blocks;
         if (K < 1) K = 1;
         std::vector<SchurParams>& groups = td->groups;
-        std::vector<int>& block_group = td->block_group;
         groups.assign((size_t)K, P);
-        block_group.assign((size_t)blocks, 0);
         CK(cudaMemsetAsync(L.gctr, 0, sizeof(int) * CTR_COUNT * (size_t)K, stream));
         CK(cudaMemsetAsync(L.gstats, 0, sizeof(unsigned long long) * ST_COUNT * (size_t)K, stream));
         const long long G = n_graphs;
@@ -473,9 +466,8 @@ int rlap_schur_eliminate(int64_t n, int64_t nnz, const int32_t* csr_ptr, const i
             Q.gblocks = (int)((long long)blocks * (g + 1) / K) - Q.gblock0;
             Q.scratch = L.gscratch + (size_t)slot0 * 3 * (size_t)L.scratch_cap;
             slot0 += Q.gblocks < NSLOT ? Q.gblocks : NSLOT;
-            for (int b = 0; b < Q.gblocks; b++) block_group[(size_t)(Q.gblock0 + b)] = (int)g;
         }
-        CK(launch_eliminate(groups.data(), (int)K, block_group.data(), blocks, o_v, o_n, flags, stream));
+        CK(launch_eliminate(groups.data(), (int)K, blocks, o_v, o_n, flags, stream));
         CK(launch_combine_groups((int)K, L.gctr, L.gstats, P.ctr, P.stats, stream));
     }
 #ifdef RLAP_DEBUG

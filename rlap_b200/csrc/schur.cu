@@ -1916,12 +1916,13 @@ cudaError_t eliminate_grid(int* blocks_out, int o_v, int o_n, int flags) {
 int eliminate_max_groups() { return TAB_GROUPS; }
 int eliminate_max_blocks() { return TAB_BLOCKS; }
 
-cudaError_t launch_eliminate(const SchurParams* groups_host, int K, const int* block_group_host, int blocks, int o_v,
-                             int o_n, int flags, cudaStream_t stream) {
+cudaError_t launch_eliminate(const SchurParams* groups_host, int K, int blocks, int o_v, int o_n, int flags,
+                             cudaStream_t stream) {
     if (K < 1 || K > TAB_GROUPS || blocks < 1 || blocks > TAB_BLOCKS) return cudaErrorInvalidValue;
     static thread_local GroupTableRaw tab;     // copied into the launch's parameter buffer by the launch call
     for (int g = 0; g < K; g++) tab.g[g] = groups_host[g];
-    for (int b = 0; b < blocks; b++) tab.bg[b] = (unsigned short)block_group_host[b];
+    for (int g = 0; g < K; g++)
+        for (int b = 0; b < groups_host[g].gblocks; b++) tab.bg[groups_host[g].gblock0 + b] = (unsigned short)g;
     void* args[] = {(void*)&tab};
     const int m = mode_index(o_v, o_n, (flags & 1) != 0);
     return cudaLaunchCooperativeKernel(mode_kernel(m), dim3(blocks), dim3(ELIM_THREADS), args,
