@@ -331,6 +331,15 @@ static SchurLayout schur_layout(long long n, long long nnz, long long G, long lo
         L.gscratch = P.scratch;
     }
     P.scratch_cap = (int)scratch_cap;
+    {
+        // staging rows of the warps' shared-memory path: one per lane of every warp the launch can have (the grid never
+        // exceeds one block per 256 vertex-views, rlap_schur_views)
+        long long sb = (V * n + 255) / 256;
+        if (sb < 1) sb = 1;
+        if (sb > MAX_SCRATCH_SLOTS) sb = MAX_SCRATCH_SLOTS;
+        P.stage = c.take<uint64_t>((size_t)sb * ELIM_WARPS * 32 * (size_t)STAGE_CAP);
+        P.stage_cap = STAGE_CAP;
+    }
     P.blocksum = c.take<long long>((size_t)scan_blocks((long long)VN));
     P.gptr = L.gptr_dev;
     P.teff = L.teff_dev;

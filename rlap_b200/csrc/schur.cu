@@ -53,8 +53,18 @@ struct ModeParams : SchurParams {
 
 // Gather the raw live entries of v into sb.A (unordered). Returns their count (group uniform);
 // *wmaxb receives the bit pattern of the largest weight. Entries beyond sb.cap are counted, not stored.
+// A fill list that a single lane has already walked (run_warp_items: the lists of all shared-memory stars of a chunk
+// are walked side by side, one per lane): `n` raw entries in global memory, and the list position the walk stopped at.
+struct StagedList {
+    const uint64_t* e = nullptr;
+    int n = 0;
+    int rest = -1;        // continue the walk here (-1: the list was walked to its end)
+    bool valid = false;   // false: nothing staged, start at the list head
+};
+
 template <bool CTA, class PT>
-__device__ int star_gather(const PT& P, int view, int v, StarBuf sb, CtaScratch* cs, uint32_t* wmaxb_out) {
+__device__ int star_gather(const PT& P, int view, int v, StarBuf sb, CtaScratch* cs, uint32_t* wmaxb_out,
+                           const StagedList stl = StagedList()) {
     const size_t vb = (size_t)view * (size_t)P.n;
     const uint8_t* st = P.state + vb;
     const int4* pool = P.pool + (size_t)view * (size_t)P.pool_cap;
@@ -98,7 +108,26 @@ __device__ int star_gather(const PT& P, int view, int v, StarBuf sb, CtaScratch*
     // appended fill entries: a linked list, walked by one warp; 32 hops are collected before the
     // (dependent) state lookups so that those run in parallel
     if (!CTA || (threadIdx.x >> 5) == 0) {
-        int p = ldcg_i32(head_p(P, vb + v));
+        int p;
+        if (!CTA && stl.valid) {
+            // the staged part: 32 entries per step, coalesced
+            for (int t0 = 0; t0 < stl.n; t0 += 32) {
+                const int t = t0 + lane;
+                const bool have = t < stl.n;
+                const uint64_t a = have ? __ldcg(stl.e + t) : 0ull;
+                const bool ok = have && !is_dead(P, view, a_nbr(a));
+                const unsigned m = __ballot_sync(RLAP_FULL_MASK, ok);
+                if (ok) {
+                    const int pos = cnt + __popc(m & lt);
+                    if (pos < sb.cap) sb.A[pos] = a;
+                    wmaxb = max(wmaxb, (uint32_t)a);
+                }
+                cnt += __popc(m);
+            }
+            p = stl.rest;
+        } else {
+            p = ldcg_i32(head_p(P, vb + v));
+        }
         while (p >= 0) {
             int4 mine = make_int4(0, 0, 0, 0);
             bool have = false;
@@ -232,13 +261,13 @@ struct LocalStats { unsigned long long fills, raw; int maxstar; unsigned nsm; };
 
 template <bool CTA, class PT>
 __device__ void eliminate_star(const PT& P, const RoundCtx& rc, int view, int v, StarBuf sb, CtaScratch* cs,
-                               LocalStats* ls, LowAppender& la) {
+                               LocalStats* ls, LowAppender& la, const StagedList stl = StagedList()) {
     const size_t vb = (size_t)view * (size_t)P.n;
     const int gs = g_size<CTA>(), r = g_rank<CTA>();
     const uint32_t view_id = P.view_base + (uint32_t)view;
     int4* pool = P.pool + (size_t)view * (size_t)P.pool_cap;
     uint32_t wmaxb;
-    int lraw = star_gather<CTA>(P, view, v, sb, cs, &wmaxb);
+    int lraw = star_gather<CTA>(P, view, v, sb, cs, &wmaxb, stl);
     if (lraw > sb.cap) {  // cannot happen for the smem tiers (callers check live); scratch tier: report
         if (r == 0) set_status(P, 6);
         lraw = 0;  // leave the vertex in place; the run is invalid anyway
@@ -906,8 +935,11 @@ __device__ void run_warp_items(const PT& P, const RoundCtx& rc, uint64_t* smem, 
     // The claim of a chunk is one returning atomic on the group's cursor; it is issued one chunk ahead (the next chunk
     // is claimed before the current one is processed), so its round trip never sits on the warp's critical path. A
     // claim past the end of the list is harmless: the cursor is only read inside the round.
+    // o_v = random: late rounds hold few, large stars (the shared-memory path takes them one after the other), so a
+    // short list is dealt out star by star instead of eight at a time
     auto chunk_size = [&](int left) {
         int c = left / (2 * nw);
+        if (P.o_v == 0) return c < 1 ? 1 : (c > 32 ? 32 : c);
         c = (c + 7) & ~7;
         return c < 8 ? 8 : (c > 32 ? 32 : c);
     };
@@ -1013,12 +1045,47 @@ __device__ void run_warp_items(const PT& P, const RoundCtx& rc, uint64_t* smem, 
         }
         // ---- shared-memory path
         unsigned msm = __ballot_sync(RLAP_FULL_MASK, kind == K_SMEM);
+        if (msm == 0) continue;
         if (lane == 0) ls->nsm += (unsigned)__popc(msm);
+        if (P.o_v == 0) {
+            // o_v = random: the late rounds hold few and large stars, and a warp that took them one after the other
+            // inside its chunk kept the whole group waiting at the round's barrier. They are listed instead and dealt
+            // out again, star by star, after the barrier (run_smem_items), next to the block-sized ones.
+            int pos0 = 0;
+            if (lane == 0) pos0 = atomicAdd(P.ctr + rc.s2slot, __popc(msm));
+            pos0 = __shfl_sync(RLAP_FULL_MASK, pos0, 0);
+            if (kind == K_SMEM) P.dl[rc.sl_top - 1 - (pos0 + __popc(msm & ((1u << lane) - 1u)))] = idx;
+            continue;
+        }
+        // The fill list of a star is a chain of dependent loads (an L2 round trip per entry); a warp that walked the
+        // lists of its shared-memory stars one after the other spent most of its time there. Every lane walks the list
+        // of its own star into a global staging row first (up to 32 chains in flight), the warp then reads the rows
+        // 32 entries at a time.
+        const bool staging = P.stage_cap > 0;
+        uint64_t* const stage = staging ? P.stage + ((size_t)blockIdx.x * ELIM_WARPS + (threadIdx.x >> 5)) * 32 * (size_t)P.stage_cap : nullptr;
+        int st_n = 0, st_rest = -1;
+        if (staging && kind == K_SMEM) {
+            const int4* pool = P.pool + (size_t)view * (size_t)P.pool_cap;
+            uint64_t* row = stage + (size_t)lane * (size_t)P.stage_cap;
+            int p = ldcg_i32(head_p(P, idx));
+            while (p >= 0 && st_n < P.stage_cap) {
+                const int4 en = __ldcg(pool + p);
+                row[st_n++] = pack_a((uint32_t)en.x, __int_as_float(en.y));
+                p = en.z;
+            }
+            st_rest = p;
+        }
+        __syncwarp();
         while (msm) {
             int k = __ffs(msm) - 1;
             msm &= msm - 1;
             unsigned int kidx = __shfl_sync(RLAP_FULL_MASK, idx, k);
-            eliminate_star<false>(P, rc, (int)(kidx / (unsigned)P.n), (int)(kidx % (unsigned)P.n), sb, cs, ls, la);
+            StagedList stl;
+            stl.valid = staging;
+            stl.e = stage + (size_t)k * (size_t)P.stage_cap;
+            stl.n = __shfl_sync(RLAP_FULL_MASK, st_n, k);
+            stl.rest = __shfl_sync(RLAP_FULL_MASK, st_rest, k);
+            eliminate_star<false>(P, rc, (int)(kidx / (unsigned)P.n), (int)(kidx % (unsigned)P.n), sb, cs, ls, la, stl);
         }
     }
 }
@@ -1030,6 +1097,56 @@ __device__ __forceinline__ StarBuf elim_cta_buf(uint64_t* smem) {
     sb.K = smem + 2 * ELIM_CAP_CTA;
     sb.cap = ELIM_CAP_CTA;
     return sb;
+}
+
+// o_v = random: the stars of the round that need the warp's shared-memory buffer (`count` of them, listed downwards
+// from dl[sl_top - 1]). Warps fetch them with one cursor, few at a time when the list is short; the fill lists of a
+// fetch are walked side by side, one per lane, into the warp's staging rows before the stars are taken in turn.
+template <class PT>
+__device__ void run_smem_items(const PT& P, const RoundCtx& rc, uint64_t* smem, CtaScratch* cs, int count,
+                               LocalStats* ls, LowAppender& la) {
+    const int nw = (int)((P.gblocks * blockDim.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    StarBuf sb = warp_region_buf(P, smem);
+    int c = count / (2 * nw);
+    c = c < 1 ? 1 : (c > 32 ? 32 : c);
+    const bool staging = P.stage_cap > 0;
+    uint64_t* const stage = staging ? P.stage + ((size_t)blockIdx.x * ELIM_WARPS + (threadIdx.x >> 5)) * 32 * (size_t)P.stage_cap : nullptr;
+    while (true) {
+        int c0 = 0;
+        if (lane == 0) c0 = atomicAdd(P.ctr + rc.c2slot, c);
+        c0 = __shfl_sync(RLAP_FULL_MASK, c0, 0);
+        if (c0 >= count) break;
+        const int it = c0 + lane;
+        unsigned int idx = 0xffffffffu;
+        if (lane < c && it < count) idx = __ldcg(P.dl + (rc.sl_top - 1 - it));
+        int st_n = 0, st_rest = -1;
+        if (staging && idx != 0xffffffffu) {
+            const int4* pool = P.pool + (size_t)(idx / (unsigned)P.n) * (size_t)P.pool_cap;
+            uint64_t* row = stage + (size_t)lane * (size_t)P.stage_cap;
+            int p = ldcg_i32(head_p(P, idx));
+            while (p >= 0 && st_n < P.stage_cap) {
+                const int4 en = __ldcg(pool + p);
+                row[st_n++] = pack_a((uint32_t)en.x, __int_as_float(en.y));
+                p = en.z;
+            }
+            st_rest = p;
+        }
+        __syncwarp();
+        unsigned m = __ballot_sync(RLAP_FULL_MASK, idx != 0xffffffffu);
+        while (m) {
+            const int k = __ffs(m) - 1;
+            m &= m - 1;
+            const unsigned int kidx = __shfl_sync(RLAP_FULL_MASK, idx, k);
+            StagedList stl;
+            stl.valid = staging;
+            stl.e = stage + (size_t)k * (size_t)P.stage_cap;
+            stl.n = __shfl_sync(RLAP_FULL_MASK, st_n, k);
+            stl.rest = __shfl_sync(RLAP_FULL_MASK, st_rest, k);
+            eliminate_star<false>(P, rc, (int)(kidx / (unsigned)P.n), (int)(kidx % (unsigned)P.n), sb, cs, ls, la, stl);
+        }
+        __syncwarp();
+    }
 }
 
 // deferred items [start, end): one block per item in shared memory; stars beyond ELIM_CAP_CTA go to the
@@ -1212,6 +1329,7 @@ __global__ void __launch_bounds__(ELIM_THREADS, mode_ctas(OV, ON, FULL)) k_elimi
     };
     int wl_start = 0;   // first unconsumed work-list item
     int dl_start = 0;
+    int sl_top = (int)((long long)P.V * P.n);   // o_v = random: top of the group's dl region (one slot of slack above)
     int rounds = 0;
     RoundCtx rc;
     LocalStats* ls = s_stats + (threadIdx.x >> 5);
@@ -1275,17 +1393,26 @@ __global__ void __launch_bounds__(ELIM_THREADS, mode_ctas(OV, ON, FULL)) k_elimi
             // items to consume were appended in the previous round
             int wl_end = wl_start + ldcg_i32(P.ctr + CTR_WCNT0 + (rounds + 2) % 3);
             if (wl_end == wl_start) break;
-            if (tid == 0) { P.ctr[CTR_WCNT0 + (rounds + 1) % 3] = 0; P.ctr[CTR_DCNT0 + (rounds + 1) % 3] = 0; P.ctr[CTR_STEAL0 + (rounds + 1) % 3] = 0; }
+            if (tid == 0) {
+                P.ctr[CTR_WCNT0 + (rounds + 1) % 3] = 0; P.ctr[CTR_DCNT0 + (rounds + 1) % 3] = 0; P.ctr[CTR_STEAL0 + (rounds + 1) % 3] = 0;
+                P.ctr[CTR_SCNT0 + (rounds + 1) % 3] = 0; P.ctr[CTR_SSTEAL0 + (rounds + 1) % 3] = 0;
+            }
             rc.sslot = CTR_STEAL0 + rounds % 3;
             rc.wl_base = wl_end; rc.wslot = CTR_WCNT0 + rounds % 3;
             rc.dl_base = dl_start; rc.dslot = CTR_DCNT0 + rounds % 3;
+            rc.sl_top = sl_top; rc.s2slot = CTR_SCNT0 + rounds % 3; rc.c2slot = CTR_SSTEAL0 + rounds % 3;
             run_warp_items(P, rc, smem, &cs, &s_next, wl_start, wl_end, ls, la);
             wl_start = wl_end;
             gsync(ST_T_D1);
-            int dl_end = dl_start + ldcg_i32(P.ctr + rc.dslot);
-            if (dl_end != dl_start) {
-                run_block_items(P, rc, smem, &cs, dl_start, dl_end, ls, la);
+            // stars too large for a lane or a register tile: the block-sized ones first (a block per star), then every
+            // warp fetches from the list of the warp-sized ones; blocks without a block-sized star start there at once
+            const int dl_end = dl_start + ldcg_i32(P.ctr + rc.dslot);
+            const int s_cnt = ldcg_i32(P.ctr + rc.s2slot);
+            if (dl_end != dl_start || s_cnt > 0) {
+                if (dl_end != dl_start) run_block_items(P, rc, smem, &cs, dl_start, dl_end, ls, la);
+                if (s_cnt > 0) run_smem_items(P, rc, smem, &cs, s_cnt, ls, la);
                 dl_start = dl_end;
+                sl_top -= s_cnt;
                 gsync(ST_T_D2);
             }
             rounds++;

@@ -26,6 +26,7 @@ constexpr int ELIM_WARPS = ELIM_THREADS / 32;
 constexpr int ELIM_CTAS_PER_SM = RLAP_ELIM_CTAS;
 constexpr int ELIM_CAP_CTA = CAP_WARP * ELIM_WARPS;   // largest star one block of the elimination kernel holds in shared memory
 
+constexpr int STAGE_CAP = 128;                        // staged fill-list entries per lane (shared-memory path of the warps)
 constexpr int NSLOT = 8;                              // blocks that own a global scratch slot
 
 // Work lists are append-only over the whole run. Items appended during round r land at
@@ -48,7 +49,9 @@ enum {
     CTR_LOWOVF1 = 17,
     CTR_STEAL0 = 18,     // elimination phase: cursor of the part of the work list any warp may fetch (18..20, by round % 3)
     CTR_BAR = 21,        // barrier of the view group: arrivals (21) and generation (22)
-    CTR_COUNT = 24
+    CTR_SCNT0 = 24,      // o_v = random: stars left to the shared-memory pass of the round (24..26, by round % 3)
+    CTR_SSTEAL0 = 27,    // ... and the cursor the warps fetch them with (27..29, by round % 3)
+    CTR_COUNT = 32
 };
 
 struct RoundCtx {
@@ -57,6 +60,9 @@ struct RoundCtx {
     int dl_base;
     int dslot;
     int sslot;     // ctr index of this round's shared-tail cursor
+    int sl_top;    // o_v = random: the round's shared-memory stars are listed downwards from dl[sl_top - 1]
+    int s2slot;    // ctr index of their count
+    int c2slot;    // ctr index of the cursor they are fetched with
 };
 enum { ST_FILLS = 0, ST_POOL_MAX = 1, ST_MAXSTAR = 2, ST_DEFERRED = 3, ST_RAW = 4,
        ST_T_INIT = 8, ST_T_A = 9, ST_T_B = 10, ST_T_C = 11, ST_T_D1 = 12, ST_T_D2 = 13,
@@ -121,6 +127,8 @@ struct SchurParams {
     // global scratch for stars larger than CAP_CTA: slot b = 3 * scratch_cap u64 for block b
     uint64_t* scratch;
     int scratch_cap;
+    uint64_t* stage;     // [blocks of the launch][ELIM_WARPS][32][STAGE_CAP]: fill lists walked ahead by single lanes
+    int stage_cap;       // STAGE_CAP, or 0 when the workspace holds no staging area
     long long* blocksum;  // scan scratch
 };
 
