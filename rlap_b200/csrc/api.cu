@@ -18,6 +18,7 @@
 #include "schur.cuh"
 
 namespace rlap {
+cudaError_t launch_hub_index(int n, const int* ptr, int* hubidx, int* count, cudaStream_t stream);
 cudaError_t launch_setup_graphs(int n, int G, const int* gptr, const long long* num_remove, int* gid, int* teff,
                                 cudaStream_t stream);
 cudaError_t eliminate_grid(int* blocks_out, int o_v, int o_n, int flags);
@@ -255,6 +256,8 @@ struct SchurLayout {
     long long G, V, pool_cap, scratch_cap;
     int* gctr;                 // [MAX_GROUPS][CTR_COUNT] control blocks of the view groups
     unsigned long long* gstats; // [MAX_GROUPS][ST_COUNT]
+    int* hubidx_dev;           // o_v = random: row of every vertex in the hub head table
+    int* hubcount_dev;
     uint64_t* gscratch;        // one scratch slot per block that may own one (NSLOT per group at most)
 };
 
@@ -340,6 +343,15 @@ static SchurLayout schur_layout(long long n, long long nnz, long long G, long lo
         P.stage = c.take<uint64_t>((size_t)sb * ELIM_WARPS * 32 * (size_t)STAGE_CAP);
         P.stage_cap = STAGE_CAP;
     }
+    {
+        // o_v = random: head table of the hubs; a vertex needs HUB_DEG input entries for a row
+        P.nhmax = (int)(nnz / HUB_DEG + 1);
+        L.hubidx_dev = c.take<int>((size_t)n);
+        L.hubcount_dev = c.take<int>(1);
+        P.hubheads = c.take<int>((size_t)V * (size_t)P.nhmax * HUB_HEADS);
+        P.hubidx = nullptr;
+        P.hubcount = nullptr;
+    }
     P.blocksum = c.take<long long>((size_t)scan_blocks((long long)VN));
     P.gptr = L.gptr_dev;
     P.teff = L.teff_dev;
@@ -417,6 +429,11 @@ int rlap_schur_eliminate(int64_t n, int64_t nnz, const int32_t* csr_ptr, const i
     CK(cudaMemsetAsync(P.stats, 0, sizeof(unsigned long long) * ST_COUNT, stream));
     CK(launch_setup_graphs((int)n, (int)n_graphs, L.gptr_dev, L.nrem_dev, n_graphs > 1 ? L.gid_dev : nullptr, L.teff_dev,
                            stream));
+    if (o_v == 0) {
+        CK(launch_hub_index((int)n, csr_ptr, L.hubidx_dev, L.hubcount_dev, stream));
+        P.hubidx = L.hubidx_dev;
+        P.hubcount = L.hubcount_dev;
+    }
     // device-side timing of the two phases (read back with the counts; no extra synchronisation)
     cudaEvent_t* ev = td->ev;
     if (!ev[0]) for (int i = 0; i < 3; i++) CK(cudaEventCreate(&ev[i]));
@@ -462,6 +479,7 @@ int rlap_schur_eliminate(int64_t n, int64_t nnz, const int32_t* csr_ptr, const i
             Q.outoff += o;                                         // phase A's (round, key) snapshots live here
             Q.pool += (size_t)v0 * (size_t)P.pool_cap;
             Q.pool_cursor += v0;
+            Q.hubheads += (size_t)v0 * (size_t)P.nhmax * HUB_HEADS;
             Q.rem += og; Q.lvl += og; Q.cntI += og; Q.ovfseg += og; Q.thresh += og;
             Q.minkey += 2 * og;                                    // [2][Vg * G] inside the [2 * V * G] array
             Q.blockcnt += o / SEL_BLOCK + 2 * (size_t)g;

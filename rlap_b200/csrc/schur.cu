@@ -107,7 +107,36 @@ __device__ int star_gather(const PT& P, int view, int v, StarBuf sb, CtaScratch*
     }
     // appended fill entries: a linked list, walked by one warp; 32 hops are collected before the
     // (dependent) state lookups so that those run in parallel
-    if (!CTA || (threadIdx.x >> 5) == 0) {
+    int hub = -1;
+    if (P.o_v == 0) hub = __ldg(P.hubidx + v);
+    if (hub >= 0) {
+        // a hub's fills: HUB_HEADS lists, one per lane of a warp
+        if (!CTA || (threadIdx.x >> 5) == 0) {
+            const int* heads = P.hubheads + ((size_t)view * (size_t)P.nhmax + (size_t)hub) * HUB_HEADS;
+            int p = ldcg_i32(heads + lane);
+            while (__any_sync(RLAP_FULL_MASK, p >= 0)) {
+                const bool have = p >= 0;
+                int4 en = make_int4(0, 0, -1, 0);
+                if (have) { en = __ldcg(pool + p); p = en.z; }
+                const bool ok = have && !is_dead(P, view, (unsigned)en.x);
+                const unsigned m = __ballot_sync(RLAP_FULL_MASK, ok);
+                int base;
+                if (CTA) {
+                    base = 0;
+                    if (lane == 0 && m) base = atomicAdd(&cs->icount, __popc(m));
+                    base = __shfl_sync(RLAP_FULL_MASK, base, 0);
+                } else {
+                    base = cnt;
+                    cnt += __popc(m);
+                }
+                if (ok) {
+                    const int pos = base + __popc(m & lt);
+                    if (pos < sb.cap) sb.A[pos] = pack_a((uint32_t)en.x, __int_as_float(en.y));
+                    wmaxb = max(wmaxb, (uint32_t)en.y);
+                }
+            }
+        }
+    } else if (!CTA || (threadIdx.x >> 5) == 0) {
         int p;
         if (!CTA && stl.valid) {
             // the staged part: 32 entries per step, coalesced
@@ -221,11 +250,21 @@ struct PendingPush {
     }
 };
 
+// the list head a fill for vertex j in pool slot `slot` is linked into (o_v = random: hubs keep HUB_HEADS lists)
+template <class PT>
+__device__ __forceinline__ int* fill_head_p(const PT& P, int view, size_t vb, int j, int slot) {
+    if (P.o_v == 0) {
+        const int h = __ldg(P.hubidx + j);
+        if (h >= 0) return P.hubheads + ((size_t)view * (size_t)P.nhmax + (size_t)h) * HUB_HEADS + ((slot >> 1) & (HUB_HEADS - 1));
+    }
+    return head_p(P, vb + j);
+}
+
 // fill edge (j,k,w): append to both endpoints; o_v = random also records the new dependency.
 // LIVE: bump the live counters of both endpoints here (the register tiles apply net deltas instead).
 // Returns false for an underflowed fill (weight 0: not created).
 template <bool LIVE, class PT>
-__device__ __forceinline__ bool push_fill(const PT& P, size_t vb, int4* pool, int j, int k, float w,
+__device__ __forceinline__ bool push_fill(const PT& P, int view, size_t vb, int4* pool, int j, int k, float w,
                                           long long slot, PendingPush* pend = nullptr) {
     if (!(w > 0.f)) {  // underflowed fill: leave two tombstones so that the pool can be read linearly
         pool[slot] = make_int4(-1, 0, -1, -1);
@@ -234,8 +273,8 @@ __device__ __forceinline__ bool push_fill(const PT& P, size_t vb, int4* pool, in
     }
     {   // both list heads are exchanged before either entry is written: the two round trips overlap
         const int s0 = (int)slot, s1 = (int)slot + 1;
-        const int n0 = atomicExch(head_p(P, vb + j), s0);
-        const int n1 = atomicExch(head_p(P, vb + k), s1);
+        const int n0 = atomicExch(fill_head_p(P, view, vb, j, s0), s0);
+        const int n1 = atomicExch(fill_head_p(P, view, vb, k, s0), s1);
         if (pend) {
             pend->e0 = make_int4(k, __float_as_int(w), n0, j);
             pend->e1 = make_int4(j, __float_as_int(w), n1, k);
@@ -322,7 +361,7 @@ __device__ void eliminate_star(const PT& P, const RoundCtx& rc, int view, int v,
                     for (int b2 = a + 1 + r; b2 < L; b2 += gs) {
                         const uint64_t eb = sb.A[b2];
                         float w = __double2float_rn(__ddiv_rn(__dmul_rn((double)a_w(ea), (double)a_w(eb)), Sf));
-                        push_fill<true>(P, vb, pool, (int)a_nbr(ea), (int)a_nbr(eb), w, slot0 + 2 * (off + (b2 - a - 1)));
+                        push_fill<true>(P, view, vb, pool, (int)a_nbr(ea), (int)a_nbr(eb), w, slot0 + 2 * (off + (b2 - a - 1)));
                     }
                 }
             } else if (coarsen) {
@@ -339,7 +378,7 @@ __device__ void eliminate_star(const PT& P, const RoundCtx& rc, int view, int v,
                     const double wm = (double)a_w(em);
                     float w = __double2float_rn(__ddiv_rn(__dmul_rn(wk, wm), __dadd_rn(wk, wm)));
                     int sl = m < koff ? m : m - 1;
-                    push_fill<true>(P, vb, pool, (int)a_nbr(em), (int)a_nbr(ek), w, slot0 + 2LL * sl);
+                    push_fill<true>(P, view, vb, pool, (int)a_nbr(em), (int)a_nbr(ek), w, slot0 + 2LL * sl);
                 }
             } else {
                 for (int m = r; m < L - 1; m += gs) {
@@ -353,7 +392,7 @@ __device__ void eliminate_star(const PT& P, const RoundCtx& rc, int view, int v,
                     if (koff >= L) koff = L - 1;
                     float w = __double2float_rn(
                         __ddiv_rn(__dmul_rn((double)a_w(em), __ull2double_rn(rem)), __ull2double_rn(S)));
-                    push_fill<true>(P, vb, pool, (int)a_nbr(em), (int)a_nbr(sb.A[koff]), w, slot0 + 2LL * m);
+                    push_fill<true>(P, view, vb, pool, (int)a_nbr(em), (int)a_nbr(sb.A[koff]), w, slot0 + 2LL * m);
                 }
             }
         }
@@ -483,7 +522,7 @@ __device__ void eliminate_star_tile(const PT& P, const RoundCtx& rc, unsigned in
             if (emit && b2 < L && tl < b2) {
                 float w = __double2float_rn(__ddiv_rn(__dmul_rn((double)a_w(a), (double)a_w(eb)), Sf));
                 long long off = (long long)tl * (2LL * L - tl - 1) / 2;
-                done = push_fill<false>(P, vb, pool, (int)a_nbr(a), (int)a_nbr(eb), w, slot0 + 2 * (off + (b2 - tl - 1)));
+                done = push_fill<false>(P, view, vb, pool, (int)a_nbr(a), (int)a_nbr(eb), w, slot0 + 2 * (off + (b2 - tl - 1)));
             }
             unsigned dm = T::ballot(done);
             if (done) delta++;
@@ -501,7 +540,7 @@ __device__ void eliminate_star_tile(const PT& P, const RoundCtx& rc, unsigned in
             const double wk = (double)a_w(ek), wm = (double)a_w(a);
             float w = __double2float_rn(__ddiv_rn(__dmul_rn(wk, wm), __dadd_rn(wk, wm)));
             int sl = tl < koff ? tl : tl - 1;
-            done = push_fill<false>(P, vb, pool, (int)a_nbr(a), (int)a_nbr(ek), w, slot0 + 2LL * sl, &pend);
+            done = push_fill<false>(P, view, vb, pool, (int)a_nbr(a), (int)a_nbr(ek), w, slot0 + 2LL * sl, &pend);
         }
         unsigned dm = T::ballot(done);
         if (done) delta++;
@@ -521,7 +560,7 @@ __device__ void eliminate_star_tile(const PT& P, const RoundCtx& rc, unsigned in
         const uint64_t ek = __shfl_sync(RLAP_FULL_MASK, a, koff, W);
         if (emit && act) {
             float w = __double2float_rn(__ddiv_rn(__dmul_rn((double)a_w(a), __ull2double_rn(rem)), __ull2double_rn(S)));
-            if (push_fill<false>(P, vb, pool, (int)a_nbr(a), (int)a_nbr(ek), w, slot0 + 2LL * tl, &pend)) {
+            if (push_fill<false>(P, view, vb, pool, (int)a_nbr(a), (int)a_nbr(ek), w, slot0 + 2LL * tl, &pend)) {
                 delta++;
                 atomicAdd(live_p(P, vb + (int)a_nbr(ek)), 1);
             }
@@ -572,6 +611,7 @@ __device__ void eliminate_star_tile(const PT& P, const RoundCtx& rc, unsigned in
 // path untouched: the lane returns false before it has modified anything.
 constexpr int LCAP = 16;          // entries per lane slot
 constexpr int LANE_NB_MAX = 48;   // longest base row a single lane scans
+static_assert(HUB_DEG > LANE_NB_MAX && HUB_DEG > 32, "lane stars and register tiles read a single fill list: hubs must never reach them");
 
 struct LaneSlot {                 // element e of this lane: A[e * 32], K[e * 32] (conflict free when the lanes of a
     uint64_t* A;                  // warp touch the same e)
@@ -724,8 +764,8 @@ __device__ bool eliminate_star_lane(const PT& P, const RoundCtx& rc, unsigned in
             return false;
         }
         const int s0 = (int)slot, s1 = (int)slot + 1;
-        const int n0 = atomicExch(head_p(P, vb + j), s0);
-        const int n1 = atomicExch(head_p(P, vb + k), s1);
+        const int n0 = atomicExch(fill_head_p(P, view, vb, j, s0), s0);
+        const int n1 = atomicExch(fill_head_p(P, view, vb, k, s0), s1);
         if (P.o_v == 0 && ldcg_u8(P.state + vb + j) == 1 && ldcg_u8(P.state + vb + k) == 1) {
             const int rj = ldcg_i32(P.rank + vb + j), rk = ldcg_i32(P.rank + vb + k);
             if (rj < rk) atomicAdd(P.blk + vb + k, 1); else atomicAdd(P.blk + vb + j, 1);
@@ -1121,7 +1161,7 @@ __device__ void run_smem_items(const PT& P, const RoundCtx& rc, uint64_t* smem, 
         unsigned int idx = 0xffffffffu;
         if (lane < c && it < count) idx = __ldcg(P.dl + (rc.sl_top - 1 - it));
         int st_n = 0, st_rest = -1;
-        if (staging && idx != 0xffffffffu) {
+        if (staging && idx != 0xffffffffu && __ldg(P.hubidx + (int)(idx % (unsigned)P.n)) < 0) {   // a hub's lists are walked by the warp
             const int4* pool = P.pool + (size_t)(idx / (unsigned)P.n) * (size_t)P.pool_cap;
             uint64_t* row = stage + (size_t)lane * (size_t)P.stage_cap;
             int p = ldcg_i32(head_p(P, idx));
@@ -1239,6 +1279,13 @@ __global__ void __launch_bounds__(ELIM_THREADS, mode_ctas(OV, ON, FULL)) k_elimi
     const long long VG = (long long)P.V * P.G;
     const bool random_order = (P.o_v == 0);
 
+    if (random_order) {
+        const long long rows = ldcg_i32(P.hubcount);
+        for (long long i = tid; i < (long long)P.V * rows * HUB_HEADS; i += nthr) {
+            const long long view = i / (rows * HUB_HEADS), r = i % (rows * HUB_HEADS);
+            P.hubheads[(view * P.nhmax) * HUB_HEADS + r] = -1;
+        }
+    }
     // ---- init: per-vertex state (ordering kernel for o_v = random: keyed Feistel rank)
     for (long long idx = tid; idx < VN; idx += nthr) {
         int view = (int)(idx / P.n), v = (int)(idx % P.n);
@@ -1964,6 +2011,22 @@ static size_t eliminate_smem_bytes(bool need_keys) {
     const size_t phases = ((size_t)6 * 1024 + (size_t)ELIM_WARPS * (224 + 160)) * sizeof(int);
     size_t m = cta > warps ? cta : warps;
     return m > phases ? m : phases;
+}
+
+// o_v = random: rows of the hub head table (vertices of at least HUB_DEG input entries), in no particular order
+__global__ void k_hub_index(int n, const int* __restrict__ ptr, int* __restrict__ hubidx, int* __restrict__ count) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    int h = -1;
+    if (ptr[v + 1] - ptr[v] >= HUB_DEG) h = atomicAdd(count, 1);
+    hubidx[v] = h;
+}
+
+cudaError_t launch_hub_index(int n, const int* ptr, int* hubidx, int* count, cudaStream_t stream) {
+    cudaError_t e = cudaMemsetAsync(count, 0, sizeof(int), stream);
+    if (e != cudaSuccess) return e;
+    k_hub_index<<<(n + 255) / 256, 256, 0, stream>>>(n, ptr, hubidx, count);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_setup_graphs(int n, int G, const int* gptr, const long long* num_remove, int* gid, int* teff,

@@ -27,6 +27,8 @@ constexpr int ELIM_CTAS_PER_SM = RLAP_ELIM_CTAS;
 constexpr int ELIM_CAP_CTA = CAP_WARP * ELIM_WARPS;   // largest star one block of the elimination kernel holds in shared memory
 
 constexpr int STAGE_CAP = 128;                        // staged fill-list entries per lane (shared-memory path of the warps)
+constexpr int HUB_DEG = 64;                           // input entries from which a vertex gets HUB_HEADS fill lists (o_v = random)
+constexpr int HUB_HEADS = 32;
 constexpr int NSLOT = 8;                              // blocks that own a global scratch slot
 
 // Work lists are append-only over the whole run. Items appended during round r land at
@@ -129,6 +131,12 @@ struct SchurParams {
     int scratch_cap;
     uint64_t* stage;     // [blocks of the launch][ELIM_WARPS][32][STAGE_CAP]: fill lists walked ahead by single lanes
     int stage_cap;       // STAGE_CAP, or 0 when the workspace holds no staging area
+    // o_v = random: vertices of at least HUB_DEG input entries keep HUB_HEADS fill lists instead of one (a fill goes to
+    // list `pool slot % HUB_HEADS`), so that a warp walks a hub's fills 32 chains at a time
+    const int* hubidx;   // [n] row of the vertex in the head table or -1 (shared by the views); nullptr for the other orders
+    const int* hubcount; // number of rows in use
+    int* hubheads;       // [V][nhmax][HUB_HEADS]
+    int nhmax;
     long long* blocksum;  // scan scratch
 };
 
