@@ -978,8 +978,11 @@ __device__ void run_warp_items(const PT& P, const RoundCtx& rc, uint64_t* smem, 
     // o_v = random: late rounds hold few, large stars (the shared-memory path takes them one after the other), so a
     // short list is dealt out star by star instead of eight at a time
     auto chunk_size = [&](int left) {
+        if (P.o_v == 0) {   // a chunk costs a fixed chain of round trips (dependency counters, work-list pushes): one chunk per warp
+            const int c1 = (left + nw - 1) / nw;
+            return c1 < 1 ? 1 : (c1 > 32 ? 32 : c1);
+        }
         int c = left / (2 * nw);
-        if (P.o_v == 0) return c < 1 ? 1 : (c > 32 ? 32 : c);
         c = (c + 7) & ~7;
         return c < 8 ? 8 : (c > 32 ? 32 : c);
     };
@@ -1148,7 +1151,7 @@ __device__ void run_smem_items(const PT& P, const RoundCtx& rc, uint64_t* smem, 
     const int nw = (int)((P.gblocks * blockDim.x) >> 5);
     const int lane = threadIdx.x & 31;
     StarBuf sb = warp_region_buf(P, smem);
-    int c = count / (2 * nw);
+    int c = (count + 2 * nw - 1) / (2 * nw);
     c = c < 1 ? 1 : (c > 32 ? 32 : c);
     const bool staging = P.stage_cap > 0;
     uint64_t* const stage = staging ? P.stage + ((size_t)blockIdx.x * ELIM_WARPS + (threadIdx.x >> 5)) * 32 * (size_t)P.stage_cap : nullptr;
@@ -1448,6 +1451,9 @@ __global__ void __launch_bounds__(ELIM_THREADS, mode_ctas(OV, ON, FULL)) k_elimi
             rc.wl_base = wl_end; rc.wslot = CTR_WCNT0 + rounds % 3;
             rc.dl_base = dl_start; rc.dslot = CTR_DCNT0 + rounds % 3;
             rc.sl_top = sl_top; rc.s2slot = CTR_SCNT0 + rounds % 3; rc.c2slot = CTR_SSTEAL0 + rounds % 3;
+#ifdef RLAP_DEBUG
+            const int items_dbg = wl_end - wl_start;
+#endif
             run_warp_items(P, rc, smem, &cs, &s_next, wl_start, wl_end, ls, la);
             wl_start = wl_end;
             gsync(ST_T_D1);
@@ -1455,6 +1461,9 @@ __global__ void __launch_bounds__(ELIM_THREADS, mode_ctas(OV, ON, FULL)) k_elimi
             // warp fetches from the list of the warp-sized ones; blocks without a block-sized star start there at once
             const int dl_end = dl_start + ldcg_i32(P.ctr + rc.dslot);
             const int s_cnt = ldcg_i32(P.ctr + rc.s2slot);
+#ifdef RLAP_DEBUG
+            const int hubs_dbg = dl_end - dl_start;
+#endif
             if (dl_end != dl_start || s_cnt > 0) {
                 if (dl_end != dl_start) run_block_items(P, rc, smem, &cs, dl_start, dl_end, ls, la);
                 if (s_cnt > 0) run_smem_items(P, rc, smem, &cs, s_cnt, ls, la);
@@ -1462,6 +1471,12 @@ __global__ void __launch_bounds__(ELIM_THREADS, mode_ctas(OV, ON, FULL)) k_elimi
                 sl_top -= s_cnt;
                 gsync(ST_T_D2);
             }
+#ifdef RLAP_DEBUG
+            if ((P.flags & 512) && tid == 0 && P.view_base == 0) {
+                printf("round %d items %d warp-sized %d block-sized %d | D1 %u D2 %u ns\n", rounds, items_dbg, s_cnt, hubs_dbg, rt[4], rt[5]);
+                for (int q = 0; q < 6; q++) rt[q] = 0;
+            }
+#endif
             rounds++;
         }
     } else {
