@@ -265,7 +265,7 @@ __device__ __forceinline__ int* fill_head_p(const PT& P, int view, size_t vb, in
 // Returns false for an underflowed fill (weight 0: not created).
 template <bool LIVE, class PT>
 __device__ __forceinline__ bool push_fill(const PT& P, int view, size_t vb, int4* pool, int j, int k, float w,
-                                          long long slot, PendingPush* pend = nullptr) {
+                                          long long slot, PendingPush* pend = nullptr, int dep = -1) {
     if (!(w > 0.f)) {  // underflowed fill: leave two tombstones so that the pool can be read linearly
         pool[slot] = make_int4(-1, 0, -1, -1);
         pool[slot + 1] = make_int4(-1, 0, -1, -1);
@@ -286,9 +286,16 @@ __device__ __forceinline__ bool push_fill(const PT& P, int view, size_t vb, int4
         if (LIVE) { atomicAdd(live_p(P, vb + j), 1); atomicAdd(live_p(P, vb + k), 1); }
     }
     if (P.o_v == 0) {
-        if (ldcg_u8(P.state + vb + j) == 1 && ldcg_u8(P.state + vb + k) == 1) {
-            int rj = ldcg_i32(P.rank + vb + j), rk = ldcg_i32(P.rank + vb + k);
-            if (rj < rk) atomicAdd(P.blk + vb + k, 1); else atomicAdd(P.blk + vb + j, 1);
+        // dep: what the caller already knows about the new dependency (-1 nothing, 0 none, 1 k waits for j, 2 j waits for k)
+        if (dep < 0) {
+            if (ldcg_u8(P.state + vb + j) == 1 && ldcg_u8(P.state + vb + k) == 1) {
+                int rj = ldcg_i32(P.rank + vb + j), rk = ldcg_i32(P.rank + vb + k);
+                if (rj < rk) atomicAdd(P.blk + vb + k, 1); else atomicAdd(P.blk + vb + j, 1);
+            }
+        } else if (dep == 1) {
+            atomicAdd(P.blk + vb + k, 1);
+        } else if (dep == 2) {
+            atomicAdd(P.blk + vb + j, 1);
         }
     }
     return true;
@@ -504,6 +511,14 @@ __device__ void eliminate_star_tile(const PT& P, const RoundCtx& rc, unsigned in
     }
     if (W == 32) T::sort_ktaq(key, tie, a, q);   // only a 32-lane tile can hold more than 16 neighbours
     else T::sort_kaq(key, a, q);
+    // o_v = random: the entry's neighbour still to be eliminated? and its rank, read here for all lanes at once instead
+    // of by every push (a neighbour of the vertex being eliminated cannot change state inside this round)
+    bool pend_mine = false;
+    int rank_mine = 0;
+    if (P.o_v == 0 && go && a != RLAP_PAD_A) {
+        pend_mine = ldcg_u8(P.state + vb + a_nbr(a)) == 1;
+        rank_mine = ldcg_i32(P.rank + vb + a_nbr(a));
+    }
     const unsigned long long C = T::incl_scan(q);
     const unsigned long long S = __shfl_sync(RLAP_FULL_MASK, C, (L > 0 ? L - 1 : 0), W);
     const long long nf = (L < 1) ? 0 : (full ? (long long)L * (L - 1) / 2 : (long long)(L - 1));
@@ -535,12 +550,18 @@ __device__ void eliminate_star_tile(const PT& P, const RoundCtx& rc, unsigned in
         if (koff >= L) koff = L - 1;
         if (koff < 0) koff = 0;
         const uint64_t ek = __shfl_sync(RLAP_FULL_MASK, a, koff, W);
+        int dep = -1;
+        if (P.o_v == 0) {
+            const bool pk = __shfl_sync(RLAP_FULL_MASK, pend_mine, koff, W);
+            const int rkk = __shfl_sync(RLAP_FULL_MASK, rank_mine, koff, W);
+            dep = (pend_mine && pk) ? (rank_mine < rkk ? 1 : 2) : 0;
+        }
         bool done = false;
         if (emit && tl < L && tl != koff) {
             const double wk = (double)a_w(ek), wm = (double)a_w(a);
             float w = __double2float_rn(__ddiv_rn(__dmul_rn(wk, wm), __dadd_rn(wk, wm)));
             int sl = tl < koff ? tl : tl - 1;
-            done = push_fill<false>(P, view, vb, pool, (int)a_nbr(a), (int)a_nbr(ek), w, slot0 + 2LL * sl, &pend);
+            done = push_fill<false>(P, view, vb, pool, (int)a_nbr(a), (int)a_nbr(ek), w, slot0 + 2LL * sl, &pend, dep);
         }
         unsigned dm = T::ballot(done);
         if (done) delta++;
@@ -558,9 +579,15 @@ __device__ void eliminate_star_tile(const PT& P, const RoundCtx& rc, unsigned in
         if (koff >= L) koff = L - 1;
         if (koff < 0) koff = 0;
         const uint64_t ek = __shfl_sync(RLAP_FULL_MASK, a, koff, W);
+        int dep = -1;
+        if (P.o_v == 0) {
+            const bool pk = __shfl_sync(RLAP_FULL_MASK, pend_mine, koff, W);
+            const int rkk = __shfl_sync(RLAP_FULL_MASK, rank_mine, koff, W);
+            dep = (pend_mine && pk) ? (rank_mine < rkk ? 1 : 2) : 0;
+        }
         if (emit && act) {
             float w = __double2float_rn(__ddiv_rn(__dmul_rn((double)a_w(a), __ull2double_rn(rem)), __ull2double_rn(S)));
-            if (push_fill<false>(P, view, vb, pool, (int)a_nbr(a), (int)a_nbr(ek), w, slot0 + 2LL * tl, &pend)) {
+            if (push_fill<false>(P, view, vb, pool, (int)a_nbr(a), (int)a_nbr(ek), w, slot0 + 2LL * tl, &pend, dep)) {
                 delta++;
                 atomicAdd(live_p(P, vb + (int)a_nbr(ek)), 1);
             }
@@ -757,7 +784,14 @@ __device__ bool eliminate_star_lane(const PT& P, const RoundCtx& rc, unsigned in
     // return) are stored while the next fill is being sampled
     int4* pp = nullptr;
     int pj = 0, pk = 0, pn0 = 0, pn1 = 0, pw = 0;
-    auto emit_fill = [&](int j, int k, float w, long long slot) -> bool {
+    // o_v = random: which neighbours are still to be eliminated (state 1), read for all entries at once: a neighbour
+    // of the vertex being eliminated cannot change state inside this round
+    unsigned pendm = 0;
+    if (P.o_v == 0) {
+#pragma unroll 4
+        for (int e = 0; e < L; e++) pendm |= (ldcg_u8(P.state + vb + a_nbr(sl.a(e))) == 1 ? 1u : 0u) << e;
+    }
+    auto emit_fill = [&](int j, int k, float w, long long slot, int ej_pos, int ek_pos) -> bool {
         if (!(w > 0.f)) {   // underflowed fill: two tombstones, the pool is read linearly at emission
             pool[slot] = make_int4(-1, 0, -1, -1);
             pool[slot + 1] = make_int4(-1, 0, -1, -1);
@@ -766,7 +800,7 @@ __device__ bool eliminate_star_lane(const PT& P, const RoundCtx& rc, unsigned in
         const int s0 = (int)slot, s1 = (int)slot + 1;
         const int n0 = atomicExch(fill_head_p(P, view, vb, j, s0), s0);
         const int n1 = atomicExch(fill_head_p(P, view, vb, k, s0), s1);
-        if (P.o_v == 0 && ldcg_u8(P.state + vb + j) == 1 && ldcg_u8(P.state + vb + k) == 1) {
+        if (P.o_v == 0 && ((pendm >> ej_pos) & (pendm >> ek_pos) & 1u)) {
             const int rj = ldcg_i32(P.rank + vb + j), rk = ldcg_i32(P.rank + vb + k);
             if (rj < rk) atomicAdd(P.blk + vb + k, 1); else atomicAdd(P.blk + vb + j, 1);
         }
@@ -797,7 +831,7 @@ __device__ bool eliminate_star_lane(const PT& P, const RoundCtx& rc, unsigned in
                 const uint64_t em = sl.a(m);
                 const double wm = (double)a_w(em);
                 const float w = __double2float_rn(__ddiv_rn(__dmul_rn(wk, wm), __dadd_rn(wk, wm)));
-                if (emit_fill((int)a_nbr(em), (int)a_nbr(ek), w, slot0 + 2LL * (m < koff ? m : m - 1))) made++;
+                if (emit_fill((int)a_nbr(em), (int)a_nbr(ek), w, slot0 + 2LL * (m < koff ? m : m - 1), m, koff)) made++;
                 else lose_one((int)a_nbr(em));
             }
             // the contraction target loses its entry to v and gains one per fill
@@ -823,7 +857,7 @@ __device__ bool eliminate_star_lane(const PT& P, const RoundCtx& rc, unsigned in
                 }
                 const int kn = (int)a_nbr(sl.a(koff));
                 const float w = __double2float_rn(__ddiv_rn(__dmul_rn((double)a_w(ej), __ull2double_rn(rem)), Sd));
-                if (emit_fill((int)a_nbr(ej), kn, w, slot0 + 2LL * j)) { made++; atomicAdd(live_p(P, vb + kn), 1); }
+                if (emit_fill((int)a_nbr(ej), kn, w, slot0 + 2LL * j, j, koff)) { made++; atomicAdd(live_p(P, vb + kn), 1); }
                 else lose_one((int)a_nbr(ej));
             }
             // the last neighbour only loses its entry
@@ -843,7 +877,7 @@ __device__ bool eliminate_star_lane(const PT& P, const RoundCtx& rc, unsigned in
         __threadfence();
         for (int e = 0; e < L; e++) {
             const int u = (int)a_nbr(sl.a(e));
-            if (ldcg_u8(P.state + vb + u) == 1) {
+            if ((pendm >> e) & 1u) {
                 const int old = atomicSub(P.blk + vb + u, 1);
                 if (old == 1) {
                     const int pos = rc.wl_base + atomicAdd(P.ctr + rc.wslot, 1);
