@@ -9,7 +9,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "_build", "liboracle.so")
+_LIB_PATH = os.environ.get("RLAP_ORACLE_LIB") or os.path.join(_HERE, "_build", "liboracle.so")   # override: experiments with an older build
 _lib = None
 
 OV = {"random": 0, "degree": 1, "coarsen": 2}
@@ -44,6 +44,8 @@ def lib():
         L.oracle_keyed_schur.restype = ctypes.c_int64
         L.oracle_ref_random_order.argtypes = [ctypes.c_int64, ctypes.c_uint64, P]
         L.oracle_rank_perm.argtypes = [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, P]
+        if hasattr(L, "oracle_star_order"):
+            L.oracle_star_order.argtypes = [P, ctypes.c_int32, ctypes.c_int, P]
         _lib = L
     return _lib
 
@@ -74,6 +76,14 @@ def philox(k0, k1, c0, c1, c2, c3):
 def rank_perm(seed, graph, view, n_g):
     out = np.zeros(n_g, dtype=np.uint32)
     lib().oracle_rank_perm(seed, graph, view, n_g, out.ctypes.data)
+    return out
+
+
+def star_order(q, o_n):
+    """o_n order (ids) of a star whose merged neighbours 0..n-1 carry the fixed-point weights q"""
+    q = np.ascontiguousarray(q, dtype=np.uint64)
+    out = np.zeros(q.shape[0], dtype=np.int32)
+    lib().oracle_star_order(q.ctypes.data, q.shape[0], ON[o_n], out.ctypes.data)
     return out
 
 

@@ -17,7 +17,7 @@
 //  (2) "keyed" mode — oracle_keyed_schur(): the same algorithm re-specified so that it can be
 //      executed in any dependency-respecting order: randomness is a pure
 //      function of (seed, view, vertex, neighbour) through Philox4x32-10, neighbour order ties
-//      are broken by id, and all in-star arithmetic is done on 64-bit fixed-point weights so
+//      stand where libstdc++'s std::sort leaves them (order_star), and all in-star arithmetic is done on 64-bit fixed-point weights so
 //      sums are order independent. The CUDA path must match this mode bit for bit
 //      (rows, columns AND fp32 weights). It shares the sampling rule (A.2: neighbour j gets one
 //      fill edge to a later neighbour k drawn with probability proportional to weight, weight
@@ -558,20 +558,17 @@ static void gather_star(const Graph& g, int32_t i, Star& s) {
 }
 
 // o_n order of the merged neighbours. Ties (the rule, not the exception: every call site of the reference uses unit
-// weights) are broken the way the reference's std::sort leaves them: libstdc++ sorts up to 16 elements with a
-// stable insertion sort, so equal weights keep their neighbour-id order (the column was sorted by row just before,
-// preconditioner.cc:275-276, 295-303); above 16 elements introsort leaves an arbitrary order, restated here as the
-// order of the per-neighbour Philox key.
+// weights) stand exactly where the reference's std::sort leaves them: the column was sorted by row just before
+// (preconditioner.cc:275-276), so the input is in neighbour-id order, and the very same call - libstdc++'s std::sort
+// with the reference's comparator (preconditioner.cc:295-303), here on the fixed-point weights - is made on it. Up to
+// 16 elements that is a stable insertion sort (ties keep the id order); above, the introsort partition loop scrambles
+// equal elements in a deterministic way, which the CUDA path restates (rlap_b200/csrc/introsort.cuh, pinned against
+// std::sort by tests/test_introsort.py).
 static void order_star(Star& s, int o_n) {
-    const bool hashed = s.m.size() > 16;
-    auto tie = [hashed](const Merged& a, const Merged& b) {
-        if (hashed && a.shuf != b.shuf) return a.shuf < b.shuf;
-        return a.nbr < b.nbr;
-    };
     if (o_n == ON_ASC)
-        std::sort(s.m.begin(), s.m.end(), [&](const Merged& a, const Merged& b) { return a.q != b.q ? a.q < b.q : tie(a, b); });
+        std::sort(s.m.begin(), s.m.end(), [](const Merged& a, const Merged& b) { return a.q < b.q; });
     else if (o_n == ON_DESC)
-        std::sort(s.m.begin(), s.m.end(), [&](const Merged& a, const Merged& b) { return a.q != b.q ? a.q > b.q : tie(a, b); });
+        std::sort(s.m.begin(), s.m.end(), [](const Merged& a, const Merged& b) { return a.q > b.q; });
     else
         std::sort(s.m.begin(), s.m.end(), [](const Merged& a, const Merged& b) { return a.shuf != b.shuf ? a.shuf < b.shuf : a.nbr < b.nbr; });
 }
@@ -830,4 +827,17 @@ extern "C" void oracle_ref_random_order(int64_t n, uint64_t rd_state, int64_t* o
     std::mt19937 g(rd.next());
     std::shuffle(node_id.begin(), node_id.end(), g);
     for (int64_t i = 0; i < n; i++) out[i] = (int64_t)node_id[(size_t)(n - 1 - i)];
+}
+
+// The o_n order of a synthetic star: merged neighbours 0..n-1 (id order) with fixed-point weights q[]. out[p] = id of
+// the neighbour at position p. Test helper for the tie rule (order_star).
+extern "C" void oracle_star_order(const uint64_t* q, int32_t n, int o_n, int32_t* out) {
+    keyed::Star s;
+    for (int32_t i = 0; i < n; i++) {
+        keyed::Merged mm;
+        mm.nbr = i; mm.q = q[i]; mm.wf = 1.0f; mm.shuf = 0; mm.usample = 0;
+        s.m.push_back(mm);
+    }
+    keyed::order_star(s, o_n);
+    for (int32_t i = 0; i < n; i++) out[i] = s.m[(size_t)i].nbr;
 }

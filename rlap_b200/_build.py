@@ -8,7 +8,7 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "_lib")
 LIB_PATH = os.path.join(LIB_DIR, "librlap_b200.so")
 SOURCES = ["api.cu", "schur.cu", "emit.cu", "ingest.cu"]
-HEADERS = ["rlap_device.cuh", "schur.cuh", "scan.cuh", "star.cuh", "ingest.cuh", os.path.join("..", "..", "include", "rlap_b200.h")]
+HEADERS = ["rlap_device.cuh", "schur.cuh", "scan.cuh", "star.cuh", "introsort.cuh", "ingest.cuh", os.path.join("..", "..", "include", "rlap_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 OBJ_DIR = os.path.join(LIB_DIR, "obj")

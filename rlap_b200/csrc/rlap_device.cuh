@@ -201,8 +201,8 @@ __device__ __forceinline__ bool rec_less(uint64_t a1, uint64_t q1, uint64_t k1, 
     bool d1 = a_dead(a1), d2 = a_dead(a2);
     if (d1 != d2) return d2;
     if (d1) return a1 < a2;
-    // asc / desc: ties by the secondary key K (equal for all entries of a star with <= 16 neighbours, the
-    // per-neighbour Philox key above: DESIGN.md §3.3), then by neighbour id
+    // asc / desc: ties by the secondary key K (equal for all entries of a star with <= 16 neighbours, above that the
+    // position std::sort's partition loop leaves the entry at: star_tie_order), then by neighbour id
     if (MODE == SORT_ASC && q1 != q2) return q1 < q2;
     if (MODE == SORT_DESC && q1 != q2) return q1 > q2;
     return (k1 != k2) ? (k1 < k2) : (a1 < a2);

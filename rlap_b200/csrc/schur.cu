@@ -307,7 +307,8 @@ struct LocalStats { unsigned long long fills, raw; int maxstar; unsigned nsm; };
 
 template <bool CTA, class PT>
 __device__ void eliminate_star(const PT& P, const RoundCtx& rc, int view, int v, StarBuf sb, CtaScratch* cs,
-                               LocalStats* ls, LowAppender& la, const StagedList stl = StagedList()) {
+                               LocalStats* ls, LowAppender& la, const StagedList stl = StagedList(),
+                               uint64_t* work = nullptr, int work_bytes = 0) {
     const size_t vb = (size_t)view * (size_t)P.n;
     const int gs = g_size<CTA>(), r = g_rank<CTA>();
     const uint32_t view_id = P.view_base + (uint32_t)view;
@@ -327,7 +328,11 @@ __device__ void eliminate_star(const PT& P, const RoundCtx& rc, int view, int v,
         const bool full = P.full;
         const bool coarsen = (P.o_v == 2) && !full;
         const int on = coarsen ? 2 : P.o_n;
-        if (!full && (on == 2 || L > 16)) {   // shuffle key; for asc / desc the tie-break of stars with > 16 neighbours
+        if (!full && on != 2 && L > 16) {     // asc / desc: equal weights among more than 16 neighbours stand the way
+            if (on == 1) star_tie_order<CTA, true>(sb, lraw, L, P2, work, work_bytes);    // std::sort leaves them
+            else star_tie_order<CTA, false>(sb, lraw, L, P2, work, work_bytes);
+        }
+        if (!full && on == 2) {               // shuffle key
             for (int i = r; i < lraw; i += gs) {
                 uint64_t a = sb.A[i];
                 if (!a_dead(a)) {
@@ -495,9 +500,14 @@ __device__ void eliminate_star_tile(const PT& P, const RoundCtx& rc, unsigned in
     const bool coarsen = (P.o_v == 2) && !full;
     const int on = coarsen ? 2 : P.o_n;
     uint64_t key = ~0ull, tie = 0;
+    // asc / desc ties among more than 16 merged neighbours: position in the arrangement std::sort's partition loop
+    // leaves (star.cuh). Only a 32-lane tile (one star per warp: the branch is warp uniform) can hold that many.
+    uint64_t tiepos = 0;
+    if (W == 32 && !full && on != 2 && L > 16)
+        tiepos = (on == 1) ? warp_tie_order<true>(q, hmask) : warp_tie_order<false>(q, hmask);
     if (live) {
-        uint64_t shuf = 0;
-        if (!full && (on == 2 || (W == 32 && L > 16))) {
+        uint64_t shuf = tiepos;
+        if (!full && on == 2) {
             uint4 x = philox4x32_10(P.k0, P.k1, (uint32_t)v, a_nbr(a), view_id, TAG_STAR);
             shuf = ((uint64_t)x.z << 32) | (uint64_t)x.w;
         }
@@ -1167,6 +1177,10 @@ __device__ void run_warp_items(const PT& P, const RoundCtx& rc, uint64_t* smem, 
     }
 }
 
+// dynamic shared memory every mode of k_eliminate has at least (phases A2 / B, eliminate_smem_bytes): what a star in the
+// global scratch slot may use as workspace
+constexpr int ELIM_SMEM_MIN_BYTES = (6 * 1024 + ELIM_WARPS * (224 + 160)) * (int)sizeof(int);
+
 __device__ __forceinline__ StarBuf elim_cta_buf(uint64_t* smem) {
     StarBuf sb;
     sb.A = smem;
@@ -1246,7 +1260,7 @@ __device__ void run_block_items(const PT& P, const RoundCtx& rc, uint64_t* smem,
             if (ldcg_i32(live_p(P, idx)) <= ELIM_CAP_CTA) continue;
             if ((j++ % nslot) != lb) continue;
             int view = (int)(idx / (unsigned)P.n), v = (int)(idx % (unsigned)P.n);
-            eliminate_star<true>(P, rc, view, v, scratch_buf(P), cs, ls, la);
+            eliminate_star<true>(P, rc, view, v, scratch_buf(P), cs, ls, la, StagedList(), smem, ELIM_SMEM_MIN_BYTES);
             __syncthreads();
         }
     }
@@ -2057,7 +2071,7 @@ static size_t eliminate_smem_bytes(bool need_keys) {
     const size_t cta = (size_t)3 * ELIM_CAP_CTA * sizeof(uint64_t);
     const size_t warps = (size_t)ELIM_WARPS * (size_t)warp_region_words(need_keys) * sizeof(uint64_t);
     // phases A2 / B: six per-segment arrays of 1 024 ints + the candidate and member buffers of every warp (224 + 160 ints)
-    const size_t phases = ((size_t)6 * 1024 + (size_t)ELIM_WARPS * (224 + 160)) * sizeof(int);
+    const size_t phases = (size_t)ELIM_SMEM_MIN_BYTES;
     size_t m = cta > warps ? cta : warps;
     return m > phases ? m : phases;
 }

@@ -4,6 +4,7 @@
 #pragma once
 #include "rlap_device.cuh"
 #include "schur.cuh"
+#include "introsort.cuh"
 
 namespace rlap {
 
@@ -98,6 +99,72 @@ __device__ int star_sort_merge(StarBuf sb, int lraw, int shift, CtaScratch* cs, 
     g_bitonic_sort_keys<CTA>(sb.A, P2);
     *P2_out = P2;
     return star_merge_sorted<CTA>(sb, lraw, shift, cs);
+}
+
+// ---------------------------------------------------------------------------------------------
+// o_n = asc / desc: ties among more than 16 merged neighbours (introsort.cuh)
+// ---------------------------------------------------------------------------------------------
+// The partition loop of libstdc++'s std::sort is sequential: ONE thread of the group runs it, out of line (its
+// explicit stack and the callers' working copies live in local memory and must not cost the persistent kernel
+// registers). Generic pointers: the arrays may be shared memory, the global scratch slot or local memory.
+template <bool DESC, class Tag>
+__device__ __noinline__ void introsort_arrange_seq(uint64_t* key, Tag* tag, int n) {
+    introsort_loop_arrange<DESC, Tag>(key, tag, n);
+}
+
+// On entry (after star_sort_merge): A sorted by neighbour with the merged-away duplicates marked dead in place,
+// Q the fixed-point weights, K = ~0 everywhere. On return the L live records stand in [0, L) in the arrangement the
+// partition loop leaves, K[i] = i for them: the o_n sort that follows (by Q, then K) is the stable sort that
+// std::__final_insertion_sort performs, i.e. exactly the order the reference's std::sort produces from the
+// id-ordered input (preconditioner.cc:275-303).
+// `work`: shared-memory workspace of `work_bytes` for a star that lives in the global scratch slot (the loop then runs
+// on a copy of the keys with 16-bit tags instead of moving records through L2), nullptr otherwise.
+template <bool CTA, bool DESC>
+__device__ void star_tie_order(StarBuf sb, int lraw, int L, int P2, uint64_t* work, int work_bytes) {
+    const int gs = g_size<CTA>(), r = g_rank<CTA>();
+    if (L < lraw) g_bitonic_sort<CTA, SORT_KEY>(sb, P2);   // K is constant: live records first, by neighbour
+    if (work != nullptr && L <= 65535 && (long long)L * 10 <= (long long)work_bytes) {
+        uint64_t* wk = work;
+        uint16_t* wt = (uint16_t*)(work + L);
+        for (int i = r; i < L; i += gs) { wk[i] = sb.Q[i]; wt[i] = (uint16_t)i; }
+        g_sync<CTA>();
+        if (r == 0) introsort_arrange_seq<DESC, uint16_t>(wk, wt, L);
+        g_sync<CTA>();
+        for (int p = r; p < L; p += gs) sb.K[wt[p]] = (uint64_t)p;
+    } else {
+        if (r == 0) introsort_arrange_seq<DESC, uint64_t>(sb.Q, sb.A, L);
+        g_sync<CTA>();
+        for (int i = r; i < L; i += gs) sb.K[i] = (uint64_t)i;
+    }
+    g_sync<CTA>();
+}
+
+// Register tile of 32 lanes (one merged neighbour per head lane of `hmask`, in neighbour order, q its fixed-point
+// weight): returns the lane's position in the same arrangement (0 for lanes outside hmask). Lane 0 runs the loop on a
+// local-memory copy. Warp-collective.
+template <bool DESC>
+__device__ __noinline__ uint32_t warp_tie_order(unsigned long long q, unsigned hmask) {
+    const int lane = threadIdx.x & 31;
+    const int L = __popc(hmask);
+    uint64_t wk[32];
+    uint8_t wt[32];
+    int j = 0;
+    for (unsigned m = hmask; m; m &= m - 1, j++) {
+        const unsigned long long v = __shfl_sync(RLAP_FULL_MASK, q, __ffs(m) - 1);
+        if (lane == 0) { wk[j] = v; wt[j] = (uint8_t)j; }
+    }
+    if (lane == 0) introsort_loop_arrange<DESC, uint8_t>(wk, wt, L);
+    __syncwarp();
+    const int ci = __popc(hmask & ((1u << lane) - 1u));
+    const bool live = (hmask >> lane) & 1u;
+    uint32_t pos = 0;
+    for (int p = 0; p < L; p++) {
+        int t = 0;
+        if (lane == 0) t = (int)wt[p];
+        t = __shfl_sync(RLAP_FULL_MASK, t, 0);
+        if (live && t == ci) pos = (uint32_t)p;
+    }
+    return pos;
 }
 
 // ---------------------------------------------------------------------------------------------

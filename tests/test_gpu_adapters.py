@@ -31,15 +31,17 @@ def test_rlap_augmentor_protocol():
 
 @pytest.mark.parametrize("o_n", ["asc", "desc", "random"])
 def test_chained_elimination_statistics_match_reference(oracle_port, o_n):
-    """10 x 5 % eliminations, o_v = random (scripts/rlap_vc_spectral.py:141-148,164): mean node count, edge count and
-    top singular value per step agree with the reference within 1 %, 3 % and 6 % (8 runs each; the systematic
-    gap of the top singular value measured with 16 runs is ~3 % under asc/desc - ties above 16 neighbours - and
-    < 1 % under o_n = random)"""
+    """10 x 5 % eliminations, o_v = random (scripts/rlap_vc_spectral.py:141-148,164): node count, edge count and top
+    singular value per step, means of 16 runs, against the reference: node counts equal, edges within 1 %, top
+    singular value within 3 % (16-run noise: the same seeds give at most 1.5 % on the sequential oracle). With the
+    tie order of std::sort restated exactly (DESIGN.md §3.3) there is no systematic gap left: over 96 further runs
+    (tools/tie_rule_experiment.py, asc) the top singular value differs by -0.5 .. +0.3 % per step at a standard error of 0.6 %,
+    the edge count by 0.01 - 0.12 %. Round 1's Philox tie rule sat 3 % low, id-order ties 7 - 11 % low."""
     from rlap_b200 import adapters, graphs
     n = 1000
     ei_np = graphs.barabasi_albert(n, 5, seed=3)
     ei = torch.from_numpy(ei_np).cuda()
-    steps, t, R = 10, int(0.05 * n), 8
+    steps, t, R = 10, int(0.05 * n), 16
 
     def run(fn_factory):
         acc = []
@@ -64,9 +66,10 @@ def test_chained_elimination_statistics_match_reference(oracle_port, o_n):
 
     got = run(lambda r: None)
     want = run(ref_factory)
-    assert np.all(np.abs(got[1] - want[1]) <= 0.01 * want[1] + 1), (got[1], want[1])
-    assert np.all(np.abs(got[2] - want[2]) <= 0.03 * want[2]), (got[2], want[2])
-    assert np.all(np.abs(got[0] - want[0]) <= 0.06 * want[0]), (got[0], want[0])
+    print(f"o_n={o_n}: top singular value GPU/reference - 1 per step: {np.round(got[0] / want[0] - 1, 4)}")
+    assert np.all(np.abs(got[1] - want[1]) <= 1), (got[1], want[1])
+    assert np.all(np.abs(got[2] - want[2]) <= 0.01 * want[2]), (got[2], want[2])
+    assert np.all(np.abs(got[0] - want[0]) <= 0.03 * want[0]), (got[0], want[0])
     assert got[2][-1] < got[2][0] and got[1][-1] < got[1][0]
 
 

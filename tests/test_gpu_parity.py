@@ -399,3 +399,38 @@ def test_degree_initial_bucket_and_first_pop_match_reference(oracle_port):
         first = np.nonzero(bucket & ~blocked)[0]
         if first.size <= n // 2:
             assert np.array_equal(np.nonzero(order == 0)[0], first), name
+
+
+@pytest.mark.parametrize("o_n", ["asc", "desc"])
+def test_tie_order_of_big_stars_matches_std_sort(oracle_port, o_n):
+    """o_n = asc / desc ties among more than 16 neighbours stand where libstdc++'s std::sort leaves them (DESIGN.md
+    §3.3): one star per tier - 24 neighbours (register tile), 100 (warp, shared memory), 600 (block, shared memory),
+    3 000 (global scratch slot, partition loop on a shared-memory copy of the keys) and 6 000 (scratch slot, in place)
+    - eliminated first under o_v = random (the centre is the vertex of rank 0), with unit weights (every key equal),
+    two-valued weights (long runs of ties) and distinct weights. Bit-exact against the oracle, whose order IS the
+    std::sort call of the reference (preconditioner.cc:295-303)."""
+    import rlap_b200
+    seed = 17
+    for leaves in (24, 100, 600, 3000, 6000):
+        n = leaves + 1
+        c = int(np.argmin(oracle_port.rank_perm(seed, 0, 0, n)))
+        others = np.array([v for v in range(n) if v != c], dtype=np.int64)
+        # a ring among the leaves as well, so that the output is more than the sampled tree
+        ring_a, ring_b = others, np.roll(others, 1)
+        src = np.concatenate([np.full(leaves, c), others, ring_a, ring_b])
+        dst = np.concatenate([others, np.full(leaves, c), ring_b, ring_a])
+        ei = np.stack([src, dst])
+        for kind in ("unit", "two", "distinct"):
+            if kind == "unit":
+                w = None
+            else:
+                a, b = np.minimum(src, dst), np.maximum(src, dst)
+                h = (a * 7919 + b * 104729) % (2 if kind == "two" else 1000003)
+                w = (1.0 + h.astype(np.float64) * (1.0 if kind == "two" else 1e-6)).astype(np.float32)
+            optr, ocol, ow = oracle_port.ingest(ei, w, n)
+            g = _gpu_graph(ei, w, n, None)
+            (row, col, wt), vp, st = rlap_b200.schur_views(g, 1, "random", o_n, seed=seed, dtype=None, return_stats=True)
+            r0, c0, w0, so = oracle_port.keyed_schur(optr, ocol, ow, 1, "random", o_n, seed=seed, return_stats=True)
+            assert so["maxlen"] == leaves, (so, leaves)               # the centre went first
+            assert np.array_equal(row.cpu().numpy(), r0) and np.array_equal(col.cpu().numpy(), c0), (leaves, kind)
+            assert np.array_equal(wt.cpu().numpy().view(np.uint32), w0.view(np.uint32)), (leaves, kind)

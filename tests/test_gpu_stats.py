@@ -33,6 +33,19 @@ def _curve_from_views(row, col, w, vp, n, L0, Ks):
     return np.array(out)
 
 
+def _modal_views(row, col, w, vp):
+    """the views whose surviving set is the most frequent one. o_v = degree on BA-100 removes the same 50 vertices in
+    all but the odd view (0 - 2 of 256, on either side); such a singleton group enters the pooled error with its
+    full one-sample error and moves the K = 256 point by 40 %, whichever side it falls on. The curves are compared on
+    the common set instead."""
+    keeps = [tuple(np.unique(col[vp[s]:vp[s + 1]]).tolist()) for s in range(len(vp) - 1)]
+    modal = max(set(keeps), key=keeps.count)
+    sel = [s for s, k in enumerate(keeps) if k == modal]
+    nvp = np.concatenate([[0], np.cumsum([vp[s + 1] - vp[s] for s in sel])])
+    cat = lambda a: np.concatenate([a[vp[s]:vp[s + 1]] for s in sel])
+    return cat(row), cat(col), cat(w), nvp
+
+
 def _ref_views(oracle_port, info, n, t, o_v, o_n, K):
     rows, cols, ws, vp = [], [], [], [0]
     for s in range(K):
@@ -68,9 +81,16 @@ def test_error_curve_matches_reference(oracle_port, o_v, o_n, t):
         back[f] = np.arange(n)
     g = rlap_b200.prepare(torch.from_numpy(np.ascontiguousarray(ei_gpu)).cuda(), None, n)
     (row, col, w), vp = rlap_b200.schur_views(g, t, o_v, o_n, num_views=K, seed=2024, shared_order=True, dtype=None)
-    cg = _curve_from_views(back[row.cpu().numpy()], back[col.cpu().numpy()], w.cpu().numpy().astype(np.float64),
-                           vp.numpy(), n, L0, KS)
-    cr = _curve_from_views(*_ref_views(oracle_port, util.edge_info(ei), n, t, o_v, o_n, K), n, L0, KS)
+    gv = (back[row.cpu().numpy()], back[col.cpu().numpy()], w.cpu().numpy().astype(np.float64), vp.numpy())
+    rv = _ref_views(oracle_port, util.edge_info(ei), n, t, o_v, o_n, K)
+    ks = KS
+    if o_v == "degree":
+        gv, rv = _modal_views(*gv), _modal_views(*rv)
+        kmin = min(len(gv[3]), len(rv[3])) - 1
+        assert kmin >= K - 8, (len(gv[3]) - 1, len(rv[3]) - 1)      # the odd view out is rare on both sides
+        ks = KS[:-1] + (kmin,)
+    cg = _curve_from_views(*gv, n, L0, ks)
+    cr = _curve_from_views(*rv, n, L0, ks)
     # coarsen: one pick per vertex instead of one per neighbour and a seed-dependent elimination set -> noisier
     lo, hi = (0.5, 1.6) if o_v == "coarsen" else (0.65, 1.35)
     assert np.all(cg / cr < hi) and np.all(cg / cr > lo), (cg, cr)
