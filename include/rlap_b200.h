@@ -81,7 +81,8 @@ int rlap_ingest(const int64_t* src, const int64_t* dst, const float* w, int64_t 
  * pure function of (seed, view id, vertex, neighbour), so results do not depend on how views are
  * sharded over GPUs). graph_ptr: HOST int64[n_graphs+1]; num_remove: HOST int64[n_graphs].
  * pool_cap: fill-edge pool entries per view (0 = default 2*nnz + 4096). scratch_cap: largest star
- * (raw live entries) the global scratch path accepts (0 = default min(n, 65536); a larger star returns
+ * (raw live entries) the global scratch path accepts (0 = default min(n, 65536); rounded up to a power of two, the
+ * size a star is padded to when it is sorted; a larger star returns
  * RLAP_ERR_STAR_TOO_LARGE and the caller retries with scratch_cap = nnz + 1, as rlap_approximate_cholesky_host does).
  * After rlap_schur_eliminate returns, view_rows (HOST int64[n_views]) holds the number of output
  * rows of every view. Synchronises `stream` once. */

@@ -154,11 +154,17 @@ int rlap_version(void) { return 1; }
 // more than e. A vertex with more incident input entries than the graph has vertices is a degenerate multigraph;
 // it is reported as RLAP_ERR_STAR_TOO_LARGE (sizing the NSLOT scratch slots for e entries each would cost 24 e
 // bytes per slot: 24 GB for the products-shaped graph).
+// The sorts pad a row to the next power of two inside its slot: the capacity is one.
+static long long pow2_at_least(long long x) {
+    long long p = 1;
+    while (p < x) p <<= 1;
+    return p;
+}
 static long long ingest_scratch_cap(long long n, long long e) {
     long long c = n > 4096 ? n : 4096;
     if (c > e) c = e;
     if (c < CAP_CTA + 1) c = CAP_CTA + 1;
-    return c;
+    return pow2_at_least(c);
 }
 
 struct IngestLayout {
@@ -271,7 +277,7 @@ static long long default_pool_cap(long long nnz) { return 2 * nnz + 4096; }
 static long long default_scratch_cap(long long n) {
     long long c = n < 65536 ? n : 65536;
     if (c < CAP_CTA + 1) c = CAP_CTA + 1;
-    return c;
+    return c;     // schur_layout rounds every capacity, the caller's too, up to a power of two
 }
 
 static SchurLayout schur_layout(long long n, long long nnz, long long G, long long V, long long pool_cap,
@@ -280,6 +286,9 @@ static SchurLayout schur_layout(long long n, long long nnz, long long G, long lo
     memset(&L, 0, sizeof(L));
     if (pool_cap <= 0) pool_cap = default_pool_cap(nnz);
     if (scratch_cap <= 0) scratch_cap = default_scratch_cap(n);
+    // a star is padded to the next power of two inside its slot (star_sort_merge): a slot of any other size would let
+    // the padding of its three arrays run into each other
+    scratch_cap = pow2_at_least(scratch_cap);
     L.G = G; L.V = V; L.pool_cap = pool_cap; L.scratch_cap = scratch_cap;
     Carver c(ws);
     SchurParams& P = L.P;

@@ -501,10 +501,12 @@ __device__ void eliminate_star_tile(const PT& P, const RoundCtx& rc, unsigned in
     const int on = coarsen ? 2 : P.o_n;
     uint64_t key = ~0ull, tie = 0;
     // asc / desc ties among more than 16 merged neighbours: position in the arrangement std::sort's partition loop
-    // leaves (star.cuh). Only a 32-lane tile (one star per warp: the branch is warp uniform) can hold that many.
+    // leaves (star.cuh). Only a 32-lane tile (one star per warp: the branch is warp uniform) can hold that many. The
+    // tile's own FCAP staged fills (128 bytes, read into `a` above) serve as its workspace.
     uint64_t tiepos = 0;
     if (W == 32 && !full && on != 2 && L > 16)
-        tiepos = (on == 1) ? warp_tie_order<true>(q, hmask) : warp_tie_order<false>(q, hmask);
+        tiepos = (on == 1) ? warp_tie_order<true>(q, hmask, (uint8_t*)const_cast<uint64_t*>(fills))
+                           : warp_tie_order<false>(q, hmask, (uint8_t*)const_cast<uint64_t*>(fills));
     if (live) {
         uint64_t shuf = tiepos;
         if (!full && on == 2) {
@@ -909,6 +911,7 @@ __device__ bool eliminate_star_lane(const PT& P, const RoundCtx& rc, unsigned in
 // ---------------------------------------------------------------------------------------------
 
 constexpr int FCAP = 16;  // fill entries per item that the chunk prologue stages in shared memory (32 x FCAP words = the lane slots)
+static_assert(FCAP * sizeof(uint64_t) >= 96, "warp_tie_order keeps 3 x 32 bytes in a tile's staged-fill slot");
 
 // Run one tier: the items whose bit is set in `mask` (lane i holds item i of the warp's chunk) are handed
 // to the 32 / W tiles of the warp, 32 / W at a time.

@@ -104,12 +104,22 @@ __device__ int star_sort_merge(StarBuf sb, int lraw, int shift, CtaScratch* cs, 
 // ---------------------------------------------------------------------------------------------
 // o_n = asc / desc: ties among more than 16 merged neighbours (introsort.cuh)
 // ---------------------------------------------------------------------------------------------
-// The partition loop of libstdc++'s std::sort is sequential: ONE thread of the group runs it, out of line (its
-// explicit stack and the callers' working copies live in local memory and must not cost the persistent kernel
-// registers). Generic pointers: the arrays may be shared memory, the global scratch slot or local memory.
-template <bool DESC, class Tag>
-__device__ __noinline__ void introsort_arrange_seq(uint64_t* key, Tag* tag, int n) {
-    introsort_loop_arrange<DESC, Tag>(key, tag, n);
+// The partition loop of libstdc++'s std::sort is run by ONE warp of the group (introsort.cuh: long ranges 32 + 32
+// elements per step, short ranges one per lane), out of line: its stacks live in local memory and must not cost the
+// persistent kernel registers. Generic pointers: the arrays may be shared memory or the global scratch slot.
+struct DeviceWarp {                 // the warp primitives introsort_loop_arrange_warp is written against
+    int lane;
+    template <class F> __device__ __forceinline__ unsigned ballot(F f) { return __ballot_sync(RLAP_FULL_MASK, f(lane)); }
+    template <class F> __device__ __forceinline__ void each(F f) { f(lane); }
+    __device__ __forceinline__ void sync() { __syncwarp(); }
+};
+// all 32 lanes of a warp call: partition passes over long ranges run 32 + 32 elements at a time, short ranges one
+// per lane (introsort.cuh)
+template <bool DESC, class Key, class Tag>
+__device__ __noinline__ void introsort_arrange_warp(Key* key, Tag* tag, int n) {
+    DeviceWarp wp;
+    wp.lane = (int)(threadIdx.x & 31);
+    introsort_loop_arrange_warp<DESC, Key, Tag, DeviceWarp>(wp, key, tag, n);
 }
 
 // On entry (after star_sort_merge): A sorted by neighbour with the merged-away duplicates marked dead in place,
@@ -128,11 +138,11 @@ __device__ void star_tie_order(StarBuf sb, int lraw, int L, int P2, uint64_t* wo
         uint16_t* wt = (uint16_t*)(work + L);
         for (int i = r; i < L; i += gs) { wk[i] = sb.Q[i]; wt[i] = (uint16_t)i; }
         g_sync<CTA>();
-        if (r == 0) introsort_arrange_seq<DESC, uint16_t>(wk, wt, L);
+        if (!CTA || threadIdx.x < 32) introsort_arrange_warp<DESC, uint64_t, uint16_t>(wk, wt, L);
         g_sync<CTA>();
         for (int p = r; p < L; p += gs) sb.K[wt[p]] = (uint64_t)p;
     } else {
-        if (r == 0) introsort_arrange_seq<DESC, uint64_t>(sb.Q, sb.A, L);
+        if (!CTA || threadIdx.x < 32) introsort_arrange_warp<DESC, uint64_t, uint64_t>(sb.Q, sb.A, L);
         g_sync<CTA>();
         for (int i = r; i < L; i += gs) sb.K[i] = (uint64_t)i;
     }
@@ -140,31 +150,34 @@ __device__ void star_tie_order(StarBuf sb, int lraw, int L, int P2, uint64_t* wo
 }
 
 // Register tile of 32 lanes (one merged neighbour per head lane of `hmask`, in neighbour order, q its fixed-point
-// weight): returns the lane's position in the same arrangement (0 for lanes outside hmask). Lane 0 runs the loop on a
-// local-memory copy. Warp-collective.
+// weight): returns the lane's position in the same arrangement (0 for lanes outside hmask). The loop only looks at
+// the order and the ties of the weights, so it runs on 8-bit keys (how many of the star's weights are smaller) and
+// 8-bit tags in `slot`: 96 bytes of shared memory the warp owns (the tile's own staged fills, consumed by now).
+// Warp-collective.
 template <bool DESC>
-__device__ __noinline__ uint32_t warp_tie_order(unsigned long long q, unsigned hmask) {
+__device__ __noinline__ uint32_t warp_tie_order(unsigned long long q, unsigned hmask, uint8_t* slot) {
     const int lane = threadIdx.x & 31;
     const int L = __popc(hmask);
-    uint64_t wk[32];
-    uint8_t wt[32];
-    int j = 0;
-    for (unsigned m = hmask; m; m &= m - 1, j++) {
-        const unsigned long long v = __shfl_sync(RLAP_FULL_MASK, q, __ffs(m) - 1);
-        if (lane == 0) { wk[j] = v; wt[j] = (uint8_t)j; }
-    }
-    if (lane == 0) introsort_loop_arrange<DESC, uint8_t>(wk, wt, L);
-    __syncwarp();
-    const int ci = __popc(hmask & ((1u << lane) - 1u));
     const bool live = (hmask >> lane) & 1u;
-    uint32_t pos = 0;
-    for (int p = 0; p < L; p++) {
-        int t = 0;
-        if (lane == 0) t = (int)wt[p];
-        t = __shfl_sync(RLAP_FULL_MASK, t, 0);
-        if (live && t == ci) pos = (uint32_t)p;
+    const int ci = __popc(hmask & ((1u << lane) - 1u));
+    int smaller = 0;
+    for (unsigned m = hmask; m; m &= m - 1) {
+        const unsigned long long v = __shfl_sync(RLAP_FULL_MASK, q, __ffs(m) - 1);
+        smaller += (v < q) ? 1 : 0;
     }
-    return pos;
+    uint8_t* k8 = slot;
+    uint8_t* t8 = slot + 32;
+    uint8_t* p8 = slot + 64;
+    __syncwarp();
+    if (live) { k8[ci] = (uint8_t)smaller; t8[ci] = (uint8_t)ci; }
+    __syncwarp();
+    DeviceWarp wp;
+    wp.lane = lane;
+    introsort_loop_arrange_warp<DESC, uint8_t, uint8_t, DeviceWarp>(wp, k8, t8, L);
+    __syncwarp();
+    if (lane < L) p8[t8[lane]] = (uint8_t)lane;
+    __syncwarp();
+    return live ? (uint32_t)p8[ci] : 0u;
 }
 
 // ---------------------------------------------------------------------------------------------
