@@ -6,6 +6,11 @@ import os
 import subprocess
 import sys
 
+import numpy as np
+import pytest
+
+from tests import util
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -39,3 +44,47 @@ def test_keyed_oracle_tie_order_is_std_sort(oracle_port):
     assert np.array_equal(q[oracle_port.star_order(q, "desc")], np.sort(q)[::-1])
     # o_n = random is untouched by the rule: shuffle keys (all equal here) then id
     assert oracle_port.star_order(one(40), "random").tolist() == list(range(40))
+
+
+@pytest.mark.parametrize("o_n", ["asc", "desc"])
+@pytest.mark.parametrize("leaves", [16, 17, 40, 200])
+def test_tie_order_is_the_one_the_reference_samples_in(oracle_port, o_n, leaves):
+    """The claimed order, read back from the UNMODIFIED reference's own output. Star K_{1,leaves} with unit weights, the
+    centre eliminated first (o_v = random with an injected random_device stream that pops it first): the reference
+    gives neighbour j (in its std::sort order) exactly one fill edge, to a LATER neighbour (preconditioner.cc:379-417).
+    So in the resulting tree every vertex but the last of the order has exactly one neighbour that stands later in the
+    order, and the last has none - for every sampling seed. A wrong order (identity above 16 elements, say) breaks
+    that within a few seeds."""
+    from oracle import ref
+    n = leaves + 1
+    centre = None
+    for rd in range(4000):
+        if int(oracle_port.ref_random_order(n, rd)[0]) == 0:
+            centre, rd_seed = 0, rd
+            break
+    assert centre == 0, "no injected stream pops vertex 0 first"
+    others = np.arange(1, n)
+    ei = np.stack([np.concatenate([np.zeros(leaves, dtype=np.int64), others]),
+                   np.concatenate([others, np.zeros(leaves, dtype=np.int64)])])
+    info = util.edge_info(ei)
+    order = oracle_port.star_order(np.full(leaves, 1 << 40, dtype=np.uint64), o_n) + 1     # vertex ids 1..leaves
+    pos = np.empty(n, dtype=np.int64)
+    pos[order] = np.arange(leaves)
+    ident = np.arange(n) - 1                                                            # the id-order hypothesis
+    run = ref.approximate_cholesky if ref.available() else oracle_port.ref_approximate_cholesky
+    wrong_hypothesis_survives = True
+    for sample_seed in range(20):
+        out = run(info, n, 1, "random", o_n, sample_seed=1 + sample_seed, rd_seed=rd_seed)
+        r, c = out[:, 0].astype(np.int64), out[:, 1].astype(np.int64)
+        assert r.shape[0] == 2 * (leaves - 1) and 0 not in set(r.tolist()) | set(c.tolist())
+        later = np.bincount(r[pos[c] > pos[r]], minlength=n)[1:]       # per vertex: neighbours later in the order
+        want = np.ones(leaves, dtype=np.int64)
+        want[order[-1] - 1] = 0
+        assert np.array_equal(later, want), (o_n, leaves, sample_seed)
+        if leaves > 16:
+            later_id = np.bincount(r[ident[c] > ident[r]], minlength=n)[1:]
+            want_id = np.ones(leaves, dtype=np.int64)
+            want_id[-1] = 0
+            wrong_hypothesis_survives &= bool(np.array_equal(later_id, want_id))
+    if leaves > 16:
+        assert not wrong_hypothesis_survives            # the test has teeth: id order is NOT what the reference does
