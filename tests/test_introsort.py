@@ -66,8 +66,20 @@ def test_tie_order_is_the_one_the_reference_samples_in(oracle_port, o_n, leaves)
     others = np.arange(1, n)
     ei = np.stack([np.concatenate([np.zeros(leaves, dtype=np.int64), others]),
                    np.concatenate([others, np.zeros(leaves, dtype=np.int64)])])
-    info = util.edge_info(ei)
-    order = oracle_port.star_order(np.full(leaves, 1 << 40, dtype=np.uint64), o_n) + 1     # vertex ids 1..leaves
+    _check_readback(oracle_port, ei, None, leaves, o_n, rd_seed, expect_id_order_refuted=leaves > 16)
+    # partial ties: two- and three-valued weights (the order is by weight, the arrangement decides inside a class)
+    rng = np.random.default_rng(leaves)
+    for nvals in (2, 3):
+        wl = rng.integers(1, nvals + 1, size=leaves).astype(np.float64)
+        _check_readback(oracle_port, ei, np.concatenate([wl, wl]), leaves, o_n, rd_seed, expect_id_order_refuted=False)
+
+
+def _check_readback(oracle_port, ei, w, leaves, o_n, rd_seed, expect_id_order_refuted):
+    from oracle import ref
+    n = leaves + 1
+    info = util.edge_info(ei, w)
+    q = np.full(leaves, 1 << 40, dtype=np.uint64) if w is None else (w[:leaves] * float(1 << 40)).astype(np.uint64)
+    order = oracle_port.star_order(q, o_n) + 1                                          # vertex ids 1..leaves
     pos = np.empty(n, dtype=np.int64)
     pos[order] = np.arange(leaves)
     ident = np.arange(n) - 1                                                            # the id-order hypothesis
@@ -81,10 +93,10 @@ def test_tie_order_is_the_one_the_reference_samples_in(oracle_port, o_n, leaves)
         want = np.ones(leaves, dtype=np.int64)
         want[order[-1] - 1] = 0
         assert np.array_equal(later, want), (o_n, leaves, sample_seed)
-        if leaves > 16:
+        if expect_id_order_refuted:
             later_id = np.bincount(r[ident[c] > ident[r]], minlength=n)[1:]
             want_id = np.ones(leaves, dtype=np.int64)
             want_id[-1] = 0
             wrong_hypothesis_survives &= bool(np.array_equal(later_id, want_id))
-    if leaves > 16:
+    if expect_id_order_refuted:
         assert not wrong_hypothesis_survives            # the test has teeth: id order is NOT what the reference does
